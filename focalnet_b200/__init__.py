@@ -1,0 +1,9 @@
+"""focalnet_b200 — B200-native (sm_100a) SS2D hot path of the FocalNet/VMamba ITS dehazing model.
+
+Only the path of SURVEY.md §8 lives here: hand-written CUDA kernels + their C ABI (``csrc/``,
+``include/ss2d_b200.h``) and the host-side mirror of the reference's operator interfaces.
+"""
+from . import _lib  # noqa: F401
+from .selective_scan import build_selective_scan_fn, scan_bwd, scan_fwd, selective_scan_fn  # noqa: F401
+
+__all__ = ["selective_scan_fn", "build_selective_scan_fn", "scan_fwd", "scan_bwd"]

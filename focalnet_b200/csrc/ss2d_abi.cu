@@ -1,0 +1,23 @@
+// ss2d_abi.cu — version / diagnostics entry points of libss2d_b200.so (see include/ss2d_b200.h).
+#include <cuda_runtime.h>
+#include "../../include/ss2d_b200.h"
+#define SS2D_STR_(x) #x
+#define SS2D_STR(x) SS2D_STR_(x)
+
+extern "C" int ss2d_abi_version(void) { return SS2D_ABI_VERSION; }
+
+extern "C" const char *ss2d_build_info(void) {
+    return "libss2d_b200 abi=1 arch=sm_100a kernels=scan_fwd,scan_bwd,cross_scan,cross_merge,cross_scan_fused,dwconv_silu "
+           "cuda=" SS2D_STR(__CUDACC_VER_MAJOR__) "." SS2D_STR(__CUDACC_VER_MINOR__);
+}
+
+extern "C" const char *ss2d_error_string(int code) {
+    switch (code) {
+        case SS2D_OK: return "ok";
+        case SS2D_EINVAL: return "invalid argument (null pointer, non-positive size, dim % ngroups != 0, dstate > 256)";
+        case SS2D_EDTYPE: return "unsupported dtype combination (out/dout must be f32 or equal to the input dtype)";
+        case SS2D_ESTRIDE: return "last-dimension stride must be 1";
+        case SS2D_EDEVICE: return "no sm_100 device";
+        default: return code > 0 ? cudaGetErrorString(static_cast<cudaError_t>(code)) : "unknown ss2d error";
+    }
+}

@@ -1,0 +1,164 @@
+// ss2d_common.cuh — device helpers shared by the SS2D kernels (sm_100a).
+//
+// Thread mapping used by every scan kernel in this library ("lanes = time, warps = channels"):
+//   * one warp owns one channel sequence (b, c); its 32 lanes own 32 consecutive blocks of T
+//     timesteps, so a warp covers a chunk of 32*T steps and walks the sequence chunk by chunk
+//     carrying the N-state running prefix;
+//   * the warps of a CTA are NW channels of the SAME (batch, group), marching over the chunks in
+//     lock-step, so the group's B/C rows are staged once per CTA in shared memory (cp.async,
+//     ping-pong over blocks of 8 states) instead of being re-read from L2 by every channel.
+// The recurrence h_t = a_t h_{t-1} + b_t is resolved with a thread-local pass, one Kogge-Stone
+// warp-shuffle scan of the (prod a, h) block aggregates, and a second thread-local pass that
+// produces the outputs — the reference does the same with cub::BlockScan plus a block-wide
+// barrier per state (selective_scan_fwd_kernel_oflex.cuh:132-171); here nothing crosses a warp.
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace ss2d {
+
+constexpr int kWarp = 32;
+constexpr float kLog2e = 1.4426950408889634f;
+
+// ---- numerics (same functions the reference evaluates, selective_scan_fwd_kernel_oflex.cuh:123-145) ----
+__device__ __forceinline__ float ex2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float softplus_ref(float x) { return x <= 20.f ? log1pf(__expf(x)) : x; }
+__device__ __forceinline__ float sigmoidf_fast(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+
+// ---- dtype conversion -------------------------------------------------------------------------------
+template <typename T> __device__ __forceinline__ float to_f32(T v);
+template <> __device__ __forceinline__ float to_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f32<__half>(__half v) { return __half2float(v); }
+template <> __device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f32(float v);
+template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ __half from_f32<__half>(float v) { return __float2half_rn(v); }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+// 16-byte vector of elements of type T
+template <typename T> struct Vec16 { static constexpr int n = 16 / sizeof(T); };
+
+// Unpack a 16-byte register quad into 16/sizeof(T) floats.
+template <typename T> __device__ __forceinline__ void unpack16(const uint4 &q, float *dst);
+template <> __device__ __forceinline__ void unpack16<float>(const uint4 &q, float *dst) {
+    dst[0] = __uint_as_float(q.x); dst[1] = __uint_as_float(q.y);
+    dst[2] = __uint_as_float(q.z); dst[3] = __uint_as_float(q.w);
+}
+template <> __device__ __forceinline__ void unpack16<__half>(const uint4 &q, float *dst) {
+    const __half2 *h = reinterpret_cast<const __half2 *>(&q);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { float2 f = __half22float2(h[i]); dst[2 * i] = f.x; dst[2 * i + 1] = f.y; }
+}
+template <> __device__ __forceinline__ void unpack16<__nv_bfloat16>(const uint4 &q, float *dst) {
+    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { dst[2 * i] = __uint_as_float(w[i] << 16); dst[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u); }
+}
+template <typename T> __device__ __forceinline__ uint4 pack16(const float *src);
+template <> __device__ __forceinline__ uint4 pack16<float>(const float *src) {
+    return make_uint4(__float_as_uint(src[0]), __float_as_uint(src[1]), __float_as_uint(src[2]), __float_as_uint(src[3]));
+}
+template <> __device__ __forceinline__ uint4 pack16<__half>(const float *src) {
+    uint4 q; __half2 *h = reinterpret_cast<__half2 *>(&q);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(src[2 * i], src[2 * i + 1]);
+    return q;
+}
+template <> __device__ __forceinline__ uint4 pack16<__nv_bfloat16>(const float *src) {
+    uint4 q; __nv_bfloat162 *h = reinterpret_cast<__nv_bfloat162 *>(&q);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(src[2 * i], src[2 * i + 1]);
+    return q;
+}
+
+// ---- global <-> register block I/O: each lane owns T consecutive elements -------------------------
+// `valid` = number of elements of this lane's block that lie inside the sequence (<=0: none).
+// vec: the row base is 16-byte aligned and the block start is a multiple of 16 bytes.
+template <typename T, int N>
+__device__ __forceinline__ void load_block(const T *__restrict__ p, float (&v)[N], int valid, bool vec, float fill = 0.f) {
+    constexpr int per = Vec16<T>::n;
+    if (vec && valid >= N) {
+#pragma unroll
+        for (int i = 0; i < N / per; ++i) {
+            uint4 q = __ldg(reinterpret_cast<const uint4 *>(p) + i);
+            unpack16<T>(q, &v[i * per]);
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < N; ++i) v[i] = i < valid ? to_f32<T>(p[i]) : fill;
+    }
+}
+template <typename T, int N>
+__device__ __forceinline__ void store_block(T *__restrict__ p, const float (&v)[N], int valid, bool vec) {
+    constexpr int per = Vec16<T>::n;
+    if (vec && valid >= N) {
+#pragma unroll
+        for (int i = 0; i < N / per; ++i) reinterpret_cast<uint4 *>(p)[i] = pack16<T>(&v[i * per]);
+    } else {
+#pragma unroll
+        for (int i = 0; i < N; ++i) if (i < valid) p[i] = from_f32<T>(v[i]);
+    }
+}
+
+// ---- cp.async (LDGSTS) -----------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+// 16-byte async copy, `bytes` (0..16) taken from global, remainder zero-filled
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem, int bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(smem_u32(smem)), "l"(gmem), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+// ---- shared-memory row layout for lane-blocked reads ----------------------------------------------
+// A row holds `chunk = 32*T` elements.  Lane j reads elements [j*T, (j+1)*T) with 16-byte LDS.  To keep
+// the eight lanes of an LDS.128 phase on distinct bank groups the stride between lane blocks (in
+// 16-byte units) must be odd, so every block is followed by one 16-byte pad when needed.
+template <typename T, int TT> struct RowLayout {
+    static constexpr int per = Vec16<T>::n;                 // elements per 16 B
+    static constexpr int units = TT / per;                  // 16-B units per lane block
+    static constexpr int stride_units = (units % 2 == 0) ? units + 1 : units;
+    static constexpr int row_units = 32 * stride_units;
+    static constexpr int row_bytes = row_units * 16;
+    // 16-B unit index inside the padded row of the q-th unpadded 16-B piece
+    __device__ __forceinline__ static int unit_of_piece(int q) { return (q / units) * stride_units + (q % units); }
+    __device__ __forceinline__ static int lane_unit(int lane) { return lane * stride_units; }
+};
+
+// Read this lane's T elements of a padded smem row into floats.
+template <typename T, int TT>
+__device__ __forceinline__ void lds_block(const unsigned char *row, int lane, float (&v)[TT]) {
+    using RL = RowLayout<T, TT>;
+    const uint4 *src = reinterpret_cast<const uint4 *>(row) + RL::lane_unit(lane);
+#pragma unroll
+    for (int i = 0; i < RL::units; ++i) unpack16<T>(src[i], &v[i * RL::per]);
+}
+
+// ---- the scan combine (a0,b0) o (a1,b1) = (a1 a0, a1 b0 + b1)  (selective_scan_common.h:93-95) ----
+// Inclusive Kogge-Stone scan over the 32 lanes of the block aggregates (P = prod a, H = local h_end).
+__device__ __forceinline__ void warp_scan_inclusive(float &P, float &H, int lane) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const float Pp = __shfl_up_sync(0xffffffffu, P, d);
+        const float Hp = __shfl_up_sync(0xffffffffu, H, d);
+        if (lane >= d) { H = fmaf(P, Hp, H); P *= Pp; }
+    }
+}
+// Mirror image for the backward's suffix scan: lane j combines with lanes j+d.
+__device__ __forceinline__ void warp_rscan_inclusive(float &P, float &H, int lane) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const float Pp = __shfl_down_sync(0xffffffffu, P, d);
+        const float Hp = __shfl_down_sync(0xffffffffu, H, d);
+        if (lane + d < 32) { H = fmaf(P, Hp, H); P *= Pp; }
+    }
+}
+
+}  // namespace ss2d

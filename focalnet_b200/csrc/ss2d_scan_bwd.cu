@@ -1,0 +1,353 @@
+// ss2d_scan_bwd.cu — selective-scan backward for sm_100a (seam S1, scan-order operands).
+//
+// Replaces selective_scan_bwd_kernel + launcher/host code (reference:
+// kernels/selective_scan/csrc/selective_scan/cusoflex/selective_scan_bwd_kernel_oflex.cuh:73-322,
+// selective_scan_oflex.cpp:245-358).  Gradient formulas (same as the reference):
+//     dx_t   = dout_t C_t + a_{t+1} dx_{t+1}                (suffix scan of (a_{t+1}, dout_t C_t))
+//     dC_t  += dout_t h_t                dB_t += dx_t dl_t u_t               (summed over the group's channels)
+//     du_t   = D dout_t + dl_t sum_n dx_t B_t
+//     ddl_t  = u_t sum_n dx_t B_t + sum_n A_n dx_t (a_t h_{t-1})             a_t h_{t-1} = h_t - dl_t u_t B_t
+//     dA_n  += sum_t dl_t dx_t (a_t h_{t-1})      dD += sum_t dout_t u_t     ddelta_t = ddl_t * softplus'(delta_t+bias)
+// Organisation: same warp-per-channel / lanes-over-time mapping as the forward (ss2d_common.cuh), chunks
+// walked right-to-left.  Chunk interiors are RECOMPUTED from the forward's fine checkpoints (h at every
+// 256 steps) — no per-step state is ever stored.  The prefix (h) and suffix (dx) recurrences are each one
+// thread-local pass + one warp-shuffle scan + one thread-local pass.  dB/dC are summed over the CTA's NW
+// channels in shared memory before ONE red.global.add.v4.f32 per 4 timesteps leaves the CTA (the
+// reference issues one scalar atomic per channel per element, 805 M at the microbench).
+#include "ss2d_common.cuh"
+#include "ss2d_scan_tile.cuh"
+#include "../../include/ss2d_b200.h"
+
+#ifndef SS2D_BWD_T
+#define SS2D_BWD_T 8
+#define SS2D_BWD_NW 8
+#define SS2D_BWD_MINB 2
+#endif
+
+namespace ss2d {
+
+__device__ __forceinline__ void red_add_v4(float *addr, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+struct BwdFlags {
+    bool vec_u, vec_delta, vec_bc, vec_dout, vec_z, vec_out, vec_dbc, vec_grad;
+};
+
+template <typename in_t, typename out_t, int T, int NW, int SB, int MINB>
+__global__ void __launch_bounds__(NW * kWarp, MINB)
+scan_bwd_kernel(const ss2d_scan_bwd_params pb, const int tiles_per_group, const BwdFlags fl) {
+    using FT = BCTile<in_t, T, SB>;
+    using RL = typename FT::RL;
+    using RLf = RowLayout<float, T>;  // staging rows for the dB/dC reduction are fp32
+    constexpr int chunk = FT::chunk;
+    constexpr int NT = NW * kWarp;
+    constexpr int ckpt_per_chunk = chunk / SS2D_CKPT_STEPS;
+    static_assert(chunk % SS2D_CKPT_STEPS == 0, "chunk must be a multiple of the checkpoint spacing");
+    extern __shared__ __align__(16) unsigned char smem[];
+    const ss2d_scan_fwd_params &p = pb.f;
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int N = (int)p.dstate;
+    const int Npad = (N + 3) & ~3;
+    const int64_t L = p.seqlen;
+    const int per_g = (int)(p.dim / p.ngroups);
+    const int tile = blockIdx.x % tiles_per_group;
+    const int bg = blockIdx.x / tiles_per_group;
+    const int g = bg % (int)p.ngroups, b = bg / (int)p.ngroups;
+    const int c_local = tile * NW + warp;
+    const bool active = c_local < per_g;
+    const int64_t c = (int64_t)g * per_g + (active ? c_local : per_g - 1);
+
+    // ---- shared memory carve-up ----
+    unsigned char *tiles = smem;                                             // 2 x B/C tile (ping-pong)
+    unsigned char *stage = smem + 2 * FT::tile_bytes;                        // [NW][2][padded chunk] fp32
+    constexpr int stage_row = RLf::row_bytes;
+    float *sA2 = reinterpret_cast<float *>(stage + NW * 2 * stage_row);      // A*log2e
+    float *sHin = sA2 + NW * Npad;                                           // h entering the current chunk
+    float *sDx = sHin + NW * Npad;                                           // dx carry from the chunk to the right
+    float *sdA = sDx + NW * Npad;                                            // [NW][N][32] per-lane dA partials
+
+    const in_t *u_row = reinterpret_cast<const in_t *>(p.u) + b * p.u_bstride + c * p.u_dstride;
+    const in_t *d_row = reinterpret_cast<const in_t *>(p.delta) + b * p.delta_bstride + c * p.delta_dstride;
+    const in_t *z_row = p.z ? reinterpret_cast<const in_t *>(p.z) + b * p.z_bstride + c * p.z_dstride : nullptr;
+    const out_t *pre_row = p.z ? reinterpret_cast<const out_t *>(p.out) + b * p.out_bstride + c * p.out_dstride : nullptr;
+    const out_t *g_row = reinterpret_cast<const out_t *>(pb.dout) + b * pb.dout_bstride + c * pb.dout_dstride;
+    const in_t *Bg = reinterpret_cast<const in_t *>(p.B) + b * p.B_bstride + g * p.B_gstride;
+    const in_t *Cg = reinterpret_cast<const in_t *>(p.C) + b * p.C_bstride + g * p.C_gstride;
+    const int64_t row = ((int64_t)b * p.dim + c) * L;
+    in_t *du_row = reinterpret_cast<in_t *>(pb.du) + row;
+    in_t *dd_row = reinterpret_cast<in_t *>(pb.ddelta) + row;
+    in_t *dz_row = pb.dz ? reinterpret_cast<in_t *>(pb.dz) + row : nullptr;
+    float *dBg = pb.dB + ((int64_t)b * p.ngroups + g) * N * L;
+    float *dCg = pb.dC + ((int64_t)b * p.ngroups + g) * N * L;
+    const float Dv = p.D ? p.D[c] : 0.f;
+    const float bias = p.delta_bias ? p.delta_bias[c] : 0.f;
+    const int n_fine = (int)((L + SS2D_CKPT_STEPS - 1) / SS2D_CKPT_STEPS);
+    const float *ck_row = p.ckpt ? p.ckpt + ((int64_t)b * p.dim + c) * n_fine * N : nullptr;
+
+    for (int n = lane; n < N; n += kWarp) {
+        sA2[warp * Npad + n] = p.A[c * N + n] * kLog2e;
+        sDx[warp * Npad + n] = 0.f;
+    }
+    for (int i = lane; i < N * kWarp; i += kWarp) sdA[warp * N * kWarp + i] = 0.f;
+
+    const int n_sb = (N + SB - 1) / SB;
+    const int n_chunks = (int)((L + chunk - 1) / chunk);
+    const int Q = n_chunks * n_sb;
+
+    stage_bc<in_t, T, SB, NT>(tiles, Bg, Cg, p.B_nstride, p.C_nstride, 0, N, (int64_t)(n_chunks - 1) * chunk, L, fl.vec_bc);
+    cp_async_commit();
+
+    float dl[T], uv[T], du[T], go[T], s[T], w[T];
+    float dsum = 0.f, qsum = 0.f, dlnext = 0.f;
+    float dl_first_right = 0.f;  // dl at the first step of the chunk to the right (0 past the end: a = 1)
+    float dD_acc = 0.f, dbias_acc = 0.f;
+
+    for (int q = 0; q < Q; ++q) {
+        const int ci = n_chunks - 1 - q / n_sb, sb = q % n_sb;
+        const int64_t t0 = (int64_t)ci * chunk;
+        cp_async_wait<0>();
+        __syncthreads();
+        if (q + 1 < Q) {
+            const int ci1 = n_chunks - 1 - (q + 1) / n_sb, sb1 = (q + 1) % n_sb;
+            stage_bc<in_t, T, SB, NT>(tiles + ((q + 1) & 1) * FT::tile_bytes, Bg, Cg, p.B_nstride, p.C_nstride,
+                                      sb1 * SB, N, (int64_t)ci1 * chunk, L, fl.vec_bc);
+            cp_async_commit();
+        }
+        const int64_t tl = t0 + lane * T;
+        const int valid = (int)min((int64_t)T, L - tl);
+        if (sb == 0) {
+            load_block<in_t, T>(u_row + tl, uv, valid, fl.vec_u);
+            load_block<in_t, T>(d_row + tl, dl, valid, fl.vec_delta);
+            load_block<out_t, T>(g_row + tl, go, valid, fl.vec_dout);
+            if (z_row) {  // out = pre * silu(z): dz and the gated upstream gradient
+                float zv[T], pre[T];
+                load_block<in_t, T>(z_row + tl, zv, valid, fl.vec_z);
+                load_block<out_t, T>(pre_row + tl, pre, valid, fl.vec_out);
+#pragma unroll
+                for (int i = 0; i < T; ++i) {
+                    const float sg = sigmoidf_fast(zv[i]);
+                    pre[i] = go[i] * pre[i] * sg * (1.f + zv[i] * (1.f - sg));
+                    go[i] *= zv[i] * sg;
+                }
+                if (active) store_block<in_t, T>(dz_row + tl, pre, valid, fl.vec_grad);
+            }
+            dsum = 0.f;
+#pragma unroll
+            for (int i = 0; i < T; ++i) {
+                float d = dl[i] + bias;
+                if (p.delta_softplus) d = softplus_ref(d);
+                d = i < valid ? d : 0.f;
+                dl[i] = d;
+                du[i] = d * uv[i];
+                s[i] = 0.f;
+                w[i] = 0.f;
+                dsum += d;
+                dD_acc = fmaf(go[i], uv[i], dD_acc);
+            }
+            // dl of the step right after this lane's block: lane+1's first, or the right chunk's first
+            dlnext = __shfl_down_sync(0xffffffffu, dl[0], 1);
+            if (lane == 31) dlnext = dl_first_right;
+            qsum = dsum - dl[0] + dlnext;
+            // h entering this chunk, from the forward's fine checkpoints
+            __syncwarp();
+            for (int n = lane; n < N; n += kWarp)
+                sHin[warp * Npad + n] = (ci > 0 && ck_row) ? ck_row[((int64_t)ci * ckpt_per_chunk - 1) * N + n] : 0.f;
+            __syncwarp();
+        }
+        const unsigned char *buf = tiles + (q & 1) * FT::tile_bytes;
+        const int n_here = min(SB, N - sb * SB);
+#pragma unroll 1
+        for (int r = 0; r < n_here; ++r) {
+            const int n = sb * SB + r;
+            const float A2 = sA2[warp * Npad + n];
+            const float An = A2 * (1.f / kLog2e);
+            float a[T], hv[T], Bv[T], Cv[T];
+            lds_block<in_t, T>(buf + r * RL::row_bytes, lane, Bv);
+#pragma unroll
+            for (int i = 0; i < T; ++i) a[i] = ex2(dl[i] * A2);
+            // ---- prefix recurrence: pass 1, warp scan, pass 2 (materialise h) ----
+            float H = du[0] * Bv[0];
+#pragma unroll
+            for (int i = 1; i < T; ++i) H = fmaf(a[i], H, du[i] * Bv[i]);
+            float P = ex2(A2 * dsum);
+            warp_scan_inclusive(P, H, lane);
+            float Pe = __shfl_up_sync(0xffffffffu, P, 1), He = __shfl_up_sync(0xffffffffu, H, 1);
+            if (lane == 0) { Pe = 1.f; He = 0.f; }
+            float h = fmaf(Pe, sHin[warp * Npad + n], He);
+#pragma unroll
+            for (int i = 0; i < T; ++i) { h = fmaf(a[i], h, du[i] * Bv[i]); hv[i] = h; }
+            // ---- suffix recurrence on (a_{t+1}, dout_t C_t) ----
+            lds_block<in_t, T>(buf + (SB + r) * RL::row_bytes, lane, Cv);
+            const float a_last = ex2(A2 * dlnext);  // a at the step following this lane's block
+            float R = go[T - 1] * Cv[T - 1];
+#pragma unroll
+            for (int i = T - 2; i >= 0; --i) R = fmaf(a[i + 1], R, go[i] * Cv[i]);
+            float Qp = ex2(A2 * qsum);
+            warp_rscan_inclusive(Qp, R, lane);
+            float Qe = __shfl_down_sync(0xffffffffu, Qp, 1), Re = __shfl_down_sync(0xffffffffu, R, 1);
+            if (lane == 31) { Qe = 1.f; Re = 0.f; }
+            const float carry = sDx[warp * Npad + n];
+            float dx = fmaf(Qe, carry, Re);  // dx at the first step right of this lane's block
+            // ---- gradients, walking the block right to left ----
+            float dBv[T], dCv[T];
+            float dA_acc = 0.f;
+#pragma unroll
+            for (int i = T - 1; i >= 0; --i) {
+                const float an = i == T - 1 ? a_last : a[i + 1];
+                dx = fmaf(an, dx, go[i] * Cv[i]);
+                dCv[i] = go[i] * hv[i];
+                dBv[i] = dx * du[i];
+                s[i] = fmaf(dx, Bv[i], s[i]);
+                const float ah = fmaf(-du[i], Bv[i], hv[i]);  // a_t h_{t-1}
+                const float pq = dx * ah;
+                w[i] = fmaf(An, pq, w[i]);
+                dA_acc = fmaf(dl[i], pq, dA_acc);
+            }
+            if (lane == 0) sDx[warp * Npad + n] = dx;  // dx at this chunk's first step -> carry for the left chunk
+            sdA[(warp * N + n) * kWarp + lane] += dA_acc;
+            // ---- dB/dC: reduce over the CTA's channels, then one vector reduction per 4 steps ----
+            if (!active) {
+#pragma unroll
+                for (int i = 0; i < T; ++i) { dBv[i] = 0.f; dCv[i] = 0.f; }
+            }
+            {
+                uint4 *dstB = reinterpret_cast<uint4 *>(stage + (warp * 2 + 0) * stage_row) + RLf::lane_unit(lane);
+                uint4 *dstC = reinterpret_cast<uint4 *>(stage + (warp * 2 + 1) * stage_row) + RLf::lane_unit(lane);
+#pragma unroll
+                for (int i = 0; i < T / 4; ++i) { dstB[i] = pack16<float>(&dBv[4 * i]); dstC[i] = pack16<float>(&dCv[4 * i]); }
+            }
+            __syncthreads();
+            for (int task = threadIdx.x; task < 2 * (chunk / 4); task += NT) {
+                const int which = task / (chunk / 4), piece = task % (chunk / 4);
+                const int unit = RLf::unit_of_piece(piece);
+                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int ww = 0; ww < NW; ++ww) {
+                    const float4 v = reinterpret_cast<const float4 *>(stage + (ww * 2 + which) * stage_row)[unit];
+                    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+                }
+                const int64_t t = t0 + (int64_t)piece * 4;
+                float *dst = (which ? dCg : dBg) + (int64_t)n * L + t;
+                if (fl.vec_dbc && t + 4 <= L) {
+                    red_add_v4(dst, acc.x, acc.y, acc.z, acc.w);
+                } else {
+                    if (t + 0 < L) atomicAdd(dst + 0, acc.x);
+                    if (t + 1 < L) atomicAdd(dst + 1, acc.y);
+                    if (t + 2 < L) atomicAdd(dst + 2, acc.z);
+                    if (t + 3 < L) atomicAdd(dst + 3, acc.w);
+                }
+            }
+            __syncthreads();
+        }
+        if (sb == n_sb - 1) {  // chunk finished: du, ddelta
+            float ddl[T];
+#pragma unroll
+            for (int i = 0; i < T; ++i) {
+                const float v = fmaf(uv[i], s[i], w[i]);
+                // softplus'(x) = sigmoid(x) = 1 - exp(-softplus(x)); exact 1 beyond the x > 20 cut-off
+                const float sg = p.delta_softplus ? -expm1f(-dl[i]) : 1.f;
+                ddl[i] = v * sg;
+                dbias_acc += i < valid ? ddl[i] : 0.f;
+                s[i] = fmaf(dl[i], s[i], Dv * go[i]);  // du
+            }
+            if (active) {
+                store_block<in_t, T>(du_row + tl, s, valid, fl.vec_grad);
+                store_block<in_t, T>(dd_row + tl, ddl, valid, fl.vec_grad);
+            }
+            dl_first_right = __shfl_sync(0xffffffffu, dl[0], 0);
+        }
+    }
+    // ---- per-channel reductions over time (and atomically over batch) ----
+    __syncwarp();
+    if (active) {
+        for (int n = 0; n < N; ++n) {
+            float v = sdA[(warp * N + n) * kWarp + lane];
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+            if (lane == 0) atomicAdd(pb.dA + c * N + n, v);
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            dD_acc += __shfl_xor_sync(0xffffffffu, dD_acc, d);
+            dbias_acc += __shfl_xor_sync(0xffffffffu, dbias_acc, d);
+        }
+        if (lane == 0) {
+            if (pb.dD) atomicAdd(pb.dD + c, dD_acc);
+            if (pb.ddelta_bias) atomicAdd(pb.ddelta_bias + c, dbias_acc);
+        }
+    }
+}
+
+static inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+template <typename in_t, typename out_t, int T, int NW, int MINB>
+static int launch_bwd(const ss2d_scan_bwd_params &pb, cudaStream_t stream) {
+    constexpr int SB = 8;
+    using FT = BCTile<in_t, T, SB>;
+    const ss2d_scan_fwd_params &p = pb.f;
+    const int per_g = (int)(p.dim / p.ngroups);
+    const int tiles = (per_g + NW - 1) / NW;
+    const int N = (int)p.dstate, Npad = (N + 3) & ~3;
+    const size_t smem = 2 * FT::tile_bytes + NW * 2 * RowLayout<float, T>::row_bytes +
+                        (3 * NW * Npad + NW * N * kWarp) * sizeof(float);
+    const int64_t ei = sizeof(in_t), eo = sizeof(out_t);
+    BwdFlags fl;
+    fl.vec_u = aligned16(p.u) && (p.u_bstride * ei) % 16 == 0 && (p.u_dstride * ei) % 16 == 0;
+    fl.vec_delta = aligned16(p.delta) && (p.delta_bstride * ei) % 16 == 0 && (p.delta_dstride * ei) % 16 == 0;
+    fl.vec_bc = aligned16(p.B) && aligned16(p.C) && (p.B_bstride * ei) % 16 == 0 && (p.B_gstride * ei) % 16 == 0 &&
+                (p.B_nstride * ei) % 16 == 0 && (p.C_bstride * ei) % 16 == 0 && (p.C_gstride * ei) % 16 == 0 &&
+                (p.C_nstride * ei) % 16 == 0;
+    fl.vec_dout = aligned16(pb.dout) && (pb.dout_bstride * eo) % 16 == 0 && (pb.dout_dstride * eo) % 16 == 0;
+    fl.vec_z = p.z && aligned16(p.z) && (p.z_bstride * ei) % 16 == 0 && (p.z_dstride * ei) % 16 == 0;
+    fl.vec_out = p.out && aligned16(p.out) && (p.out_bstride * eo) % 16 == 0 && (p.out_dstride * eo) % 16 == 0;
+    fl.vec_dbc = aligned16(pb.dB) && aligned16(pb.dC) && p.seqlen % 4 == 0;
+    // du / ddelta / dz rows are contiguous (batch, dim, L)
+    fl.vec_grad = aligned16(pb.du) && aligned16(pb.ddelta) && (!pb.dz || aligned16(pb.dz)) && (p.seqlen * ei) % 16 == 0;
+    auto kern = scan_bwd_kernel<in_t, out_t, T, NW, SB, MINB>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    const int64_t grid = p.batch * p.ngroups * tiles;
+    kern<<<(unsigned)grid, NW * kWarp, smem, stream>>>(pb, tiles, fl);
+    return (int)cudaGetLastError();
+}
+
+}  // namespace ss2d
+
+extern "C" int ss2d_selective_scan_bwd(const ss2d_scan_bwd_params *pp, void *stream) {
+    if (!pp) return SS2D_EINVAL;
+    ss2d_scan_bwd_params pb = *pp;
+    const ss2d_scan_fwd_params &p = pb.f;
+    if (!p.u || !p.delta || !p.A || !p.B || !p.C || !pb.dout || !pb.du || !pb.ddelta || !pb.dA || !pb.dB || !pb.dC)
+        return SS2D_EINVAL;
+    if (p.batch <= 0 || p.dim <= 0 || p.seqlen <= 0 || p.dstate <= 0 || p.ngroups <= 0) return SS2D_EINVAL;
+    if (p.dim % p.ngroups != 0 || p.dstate > SS2D_MAX_DSTATE) return SS2D_EINVAL;
+    if ((p.D && !pb.dD) || (p.delta_bias && !pb.ddelta_bias)) return SS2D_EINVAL;
+    if (p.z && (!pb.dz || !p.out)) return SS2D_EINVAL;
+    if (p.out_dtype != SS2D_F32 && p.out_dtype != p.in_dtype) return SS2D_EDTYPE;
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    if (!p.ckpt && p.seqlen > SS2D_CKPT_STEPS) {
+        // Foreign caller that only kept the reference's coarse x: rebuild the fine checkpoints with a
+        // states-only forward sweep (out == NULL) into the caller's scratch buffer.
+        if (!pb.ckpt_scratch) return SS2D_EINVAL;
+        ss2d_scan_fwd_params f = p;
+        f.out = nullptr; f.out_z = nullptr; f.z = nullptr; f.x = nullptr; f.ckpt = pb.ckpt_scratch;
+        f.out_dtype = SS2D_F32;
+        const int rc = ss2d_selective_scan_fwd(&f, stream);
+        if (rc != 0) return rc;
+        pb.f.ckpt = pb.ckpt_scratch;
+    }
+    using namespace ss2d;
+    constexpr int T = SS2D_BWD_T, NW = SS2D_BWD_NW, MINB = SS2D_BWD_MINB;
+    switch (p.in_dtype) {
+        case SS2D_F32: return launch_bwd<float, float, T, NW, MINB>(pb, s);
+        case SS2D_F16:
+            return p.out_dtype == SS2D_F32 ? launch_bwd<__half, float, T, NW, MINB>(pb, s)
+                                           : launch_bwd<__half, __half, T, NW, MINB>(pb, s);
+        case SS2D_BF16:
+            return p.out_dtype == SS2D_F32 ? launch_bwd<__nv_bfloat16, float, T, NW, MINB>(pb, s)
+                                           : launch_bwd<__nv_bfloat16, __nv_bfloat16, T, NW, MINB>(pb, s);
+        default: return SS2D_EDTYPE;
+    }
+}

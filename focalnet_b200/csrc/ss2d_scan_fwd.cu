@@ -1,0 +1,239 @@
+// ss2d_scan_fwd.cu — selective-scan forward for sm_100a (seam S1, scan-order operands).
+//
+// Replaces selective_scan_fwd_kernel + its launcher/host code
+// (reference: kernels/selective_scan/csrc/selective_scan/cusoflex/selective_scan_fwd_kernel_oflex.cuh:67-211,
+//  selective_scan_oflex.cpp:157-243).  Same maths:
+//     dl_t = softplus(delta_t + bias_c)            a_{t,n} = exp2(dl_t * A_{c,n} * log2 e)
+//     h_{t,n} = a_{t,n} h_{t-1,n} + dl_t u_t B_{n,t}        out_t = D_c u_t + sum_n C_{n,t} h_{t,n}
+// Different organisation (see ss2d_common.cuh): one warp per channel, CTA = NW channels of one
+// (batch, group); B/C rows of the group staged once per CTA by cp.async in a 2-deep ping-pong over
+// blocks of SB states; no block-wide scan, one __syncthreads per state block.
+//
+// HBM traffic per launch (the figure bench.py uses):  s_in*(2*B*Dm*L + 2*B*G*N*L) + s_out*B*Dm*L
+//   + 4*B*Dm*(ceil(L/2048)*2N + ceil(L/256)*N)   [checkpoints]
+#include "ss2d_common.cuh"
+#include "ss2d_scan_tile.cuh"
+#include "../../include/ss2d_b200.h"
+
+namespace ss2d {
+
+struct FwdFlags {
+    bool vec_u, vec_delta, vec_bc, vec_out, vec_z;
+};
+
+// One state of one chunk for this lane's T steps.  `FIRST`/`n` index the carry arrays.
+//   pass 1 keeps the running product and the local state of every step (Pcum_i, hloc_i) in the registers
+//   that held a_i and b_i, so pass 2 (h_i = Pcum_i * h_in + hloc_i) has no serial dependency.
+template <typename in_t, int T, int SLOTS>
+__device__ __forceinline__ void fwd_one_state(const unsigned char *Brow, const unsigned char *Crow, int lane,
+                                              const float (&dl)[T], const float (&du)[T], float (&y)[T], float A2,
+                                              float *ck /* [SLOTS] strided by ck_stride */, int ck_stride, float *sP) {
+    float a[T], hl[T];
+    {
+        float Bv[T];
+        lds_block<in_t, T>(Brow, lane, Bv);
+#pragma unroll
+        for (int i = 0; i < T; ++i) { a[i] = ex2(dl[i] * A2); hl[i] = du[i] * Bv[i]; }
+    }
+#pragma unroll
+    for (int i = 1; i < T; ++i) { hl[i] = fmaf(a[i], hl[i - 1], hl[i]); a[i] *= a[i - 1]; }
+    float P = a[T - 1], H = hl[T - 1];
+    warp_scan_inclusive(P, H, lane);
+    float Pe = __shfl_up_sync(0xffffffffu, P, 1), He = __shfl_up_sync(0xffffffffu, H, 1);
+    if (lane == 0) { Pe = 1.f; He = 0.f; }
+    const float carry = ck[(SLOTS - 1) * ck_stride];  // h at the end of the previous chunk
+    const float hin = fmaf(Pe, carry, He);
+    float Cv[T];
+    lds_block<in_t, T>(Crow, lane, Cv);
+    float h = hin;
+#pragma unroll
+    for (int i = 0; i < T; ++i) { h = fmaf(a[i], hin, hl[i]); y[i] = fmaf(Cv[i], h, y[i]); }
+    // lanes whose block ends on a checkpoint boundary publish h there (the last slot is the chunk carry)
+    constexpr int lanes_per_slot = kWarp / SLOTS;
+    if ((lane + 1) % lanes_per_slot == 0) ck[((lane + 1) / lanes_per_slot - 1) * ck_stride] = h;
+    if (lane == kWarp - 1) *sP *= P;
+}
+
+template <typename in_t, typename out_t, int T, int NW, int SB>
+__global__ void __launch_bounds__(NW * kWarp, 2)
+scan_fwd_kernel(const ss2d_scan_fwd_params p, const int tiles_per_group, const FwdFlags fl) {
+    using FT = BCTile<in_t, T, SB>;
+    using RL = typename FT::RL;
+    constexpr int chunk = FT::chunk;
+    constexpr int NT = NW * kWarp;
+    constexpr int SLOTS = chunk / SS2D_CKPT_STEPS;  // fine checkpoints per chunk
+    static_assert(chunk % SS2D_CKPT_STEPS == 0 && SS2D_REF_CHUNK % chunk == 0, "chunk must tile the checkpoint grids");
+    extern __shared__ __align__(16) unsigned char smem[];
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int N = (int)p.dstate;
+    const int Npad = (N + 3) & ~3;
+    const int64_t L = p.seqlen;
+    const int per_g = (int)(p.dim / p.ngroups);
+    const int tile = blockIdx.x % tiles_per_group;
+    const int bg = blockIdx.x / tiles_per_group;
+    const int g = bg % (int)p.ngroups, b = bg / (int)p.ngroups;
+    const int c_local = tile * NW + warp;
+    const bool active = c_local < per_g;
+    const int64_t c = (int64_t)g * per_g + (active ? c_local : per_g - 1);
+
+    unsigned char *tiles = smem;
+    float *sA2 = reinterpret_cast<float *>(smem + 2 * FT::tile_bytes) + warp * Npad;  // A * log2(e)
+    float *sP = reinterpret_cast<float *>(smem + 2 * FT::tile_bytes) + NW * Npad + warp * Npad;  // running prod a (for x)
+    float *sCk = reinterpret_cast<float *>(smem + 2 * FT::tile_bytes) + 2 * NW * Npad + warp * SLOTS * Npad;  // [SLOTS][Npad]
+
+    const in_t *u_row = reinterpret_cast<const in_t *>(p.u) + b * p.u_bstride + c * p.u_dstride;
+    const in_t *d_row = reinterpret_cast<const in_t *>(p.delta) + b * p.delta_bstride + c * p.delta_dstride;
+    const in_t *z_row = p.z ? reinterpret_cast<const in_t *>(p.z) + b * p.z_bstride + c * p.z_dstride : nullptr;
+    const in_t *Bg = reinterpret_cast<const in_t *>(p.B) + b * p.B_bstride + g * p.B_gstride;
+    const in_t *Cg = reinterpret_cast<const in_t *>(p.C) + b * p.C_bstride + g * p.C_gstride;
+    out_t *o_row = p.out ? reinterpret_cast<out_t *>(p.out) + b * p.out_bstride + c * p.out_dstride : nullptr;
+    out_t *oz_row = p.out_z ? reinterpret_cast<out_t *>(p.out_z) + b * p.out_bstride + c * p.out_dstride : nullptr;
+    const float Dv = p.D ? p.D[c] : 0.f;
+    const float bias = p.delta_bias ? p.delta_bias[c] : 0.f;
+
+    for (int n = lane; n < N; n += kWarp) {
+        sA2[n] = p.A[c * N + n] * kLog2e;
+        sP[n] = 1.f;
+        sCk[(SLOTS - 1) * Npad + n] = 0.f;
+    }
+
+    const int n_sb = (N + SB - 1) / SB;
+    const int n_chunks = (int)((L + chunk - 1) / chunk);
+    const int Q = n_chunks * n_sb;
+    const int n_fine = (int)((L + SS2D_CKPT_STEPS - 1) / SS2D_CKPT_STEPS);
+    const int n_ref = (int)((L + SS2D_REF_CHUNK - 1) / SS2D_REF_CHUNK);
+
+    stage_bc<in_t, T, SB, NT>(tiles, Bg, Cg, p.B_nstride, p.C_nstride, 0, N, 0, L, fl.vec_bc);
+    cp_async_commit();
+
+    float dl[T], du[T], y[T];
+    for (int q = 0; q < Q; ++q) {
+        const int ci = q / n_sb, sb = q % n_sb;
+        const int64_t t0 = (int64_t)ci * chunk;
+        cp_async_wait<0>();
+        __syncthreads();  // tile q visible to everyone; everyone is done with the buffer tile q+1 will overwrite
+        if (q + 1 < Q) {
+            const int ci1 = (q + 1) / n_sb, sb1 = (q + 1) % n_sb;
+            stage_bc<in_t, T, SB, NT>(tiles + ((q + 1) & 1) * FT::tile_bytes, Bg, Cg, p.B_nstride, p.C_nstride,
+                                      sb1 * SB, N, (int64_t)ci1 * chunk, L, fl.vec_bc);
+            cp_async_commit();
+        }
+        const int64_t tl = t0 + lane * T;                 // first timestep of this lane's block
+        const int valid = (int)min((int64_t)T, L - tl);   // may be <= 0
+        if (sb == 0) {
+            float uv[T];
+            load_block<in_t, T>(u_row + tl, uv, valid, fl.vec_u);
+            load_block<in_t, T>(d_row + tl, dl, valid, fl.vec_delta);
+            if (tl + chunk < L) {  // pull the next chunk's u / delta lines into L2 while this chunk computes
+                prefetch_l2(u_row + tl + chunk);
+                prefetch_l2(d_row + tl + chunk);
+            }
+#pragma unroll
+            for (int i = 0; i < T; ++i) {
+                float d = dl[i] + bias;
+                if (p.delta_softplus) d = softplus_ref(d);
+                d = i < valid ? d : 0.f;  // identity element past the end (fwd_kernel_oflex.cuh:146-150)
+                dl[i] = d;
+                du[i] = d * uv[i];
+                y[i] = Dv * uv[i];
+            }
+        }
+        const unsigned char *buf = tiles + (q & 1) * FT::tile_bytes;
+        if (N - sb * SB >= SB) {
+#pragma unroll
+            for (int r = 0; r < SB; ++r)
+                fwd_one_state<in_t, T, SLOTS>(buf + r * RL::row_bytes, buf + (SB + r) * RL::row_bytes, lane, dl, du, y,
+                                             sA2[sb * SB + r], sCk + sb * SB + r, Npad, sP + sb * SB + r);
+        } else {
+#pragma unroll 1
+            for (int r = 0; r < N - sb * SB; ++r)
+                fwd_one_state<in_t, T, SLOTS>(buf + r * RL::row_bytes, buf + (SB + r) * RL::row_bytes, lane, dl, du, y,
+                                             sA2[sb * SB + r], sCk + sb * SB + r, Npad, sP + sb * SB + r);
+        }
+        if (sb == n_sb - 1) {  // chunk finished
+            __syncwarp();
+            if (active) {
+                if (o_row) {
+                    store_block<out_t, T>(o_row + tl, y, valid, fl.vec_out);
+                    if (z_row) {
+                        float zv[T];
+                        load_block<in_t, T>(z_row + tl, zv, valid, fl.vec_z);
+#pragma unroll
+                        for (int i = 0; i < T; ++i) y[i] *= zv[i] * sigmoidf_fast(zv[i]);
+                        store_block<out_t, T>(oz_row + tl, y, valid, fl.vec_out);
+                    }
+                }
+                const int64_t t_end = min(L, t0 + chunk);
+                const bool last = ci == n_chunks - 1;
+                if (p.ckpt) {
+                    float *dst = p.ckpt + ((int64_t)b * p.dim + c) * n_fine * N;
+#pragma unroll
+                    for (int sl = 0; sl < SLOTS; ++sl) {
+                        const int f = ci * SLOTS + sl;
+                        if (f < n_fine)
+                            for (int n = lane; n < N; n += kWarp) dst[(int64_t)f * N + n] = sCk[sl * Npad + n];
+                    }
+                }
+                if (p.x && (t_end % SS2D_REF_CHUNK == 0 || last)) {
+                    float2 *dst = reinterpret_cast<float2 *>(p.x) +
+                                  (((int64_t)b * p.dim + c) * n_ref + (t_end - 1) / SS2D_REF_CHUNK) * N;
+                    for (int n = lane; n < N; n += kWarp) dst[n] = make_float2(sP[n], sCk[(SLOTS - 1) * Npad + n]);
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+
+static inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+template <typename in_t, typename out_t>
+static int launch_fwd(const ss2d_scan_fwd_params &p, cudaStream_t stream) {
+    constexpr int T = 16, NW = 8, SB = 8;
+    using FT = BCTile<in_t, T, SB>;
+    const int per_g = (int)(p.dim / p.ngroups);
+    const int tiles = (per_g + NW - 1) / NW;
+    const int Npad = ((int)p.dstate + 3) & ~3;
+    const size_t smem = 2 * FT::tile_bytes + (2 + FT::chunk / SS2D_CKPT_STEPS) * NW * Npad * sizeof(float);
+    const int64_t ei = sizeof(in_t), eo = sizeof(out_t);
+    FwdFlags fl;
+    fl.vec_u = aligned16(p.u) && (p.u_bstride * ei) % 16 == 0 && (p.u_dstride * ei) % 16 == 0;
+    fl.vec_delta = aligned16(p.delta) && (p.delta_bstride * ei) % 16 == 0 && (p.delta_dstride * ei) % 16 == 0;
+    fl.vec_bc = aligned16(p.B) && aligned16(p.C) && (p.B_bstride * ei) % 16 == 0 && (p.B_gstride * ei) % 16 == 0 &&
+                (p.B_nstride * ei) % 16 == 0 && (p.C_bstride * ei) % 16 == 0 && (p.C_gstride * ei) % 16 == 0 &&
+                (p.C_nstride * ei) % 16 == 0;
+    fl.vec_out = aligned16(p.out) && (!p.out_z || aligned16(p.out_z)) && (p.out_bstride * eo) % 16 == 0 &&
+                 (p.out_dstride * eo) % 16 == 0;
+    fl.vec_z = p.z && aligned16(p.z) && (p.z_bstride * ei) % 16 == 0 && (p.z_dstride * ei) % 16 == 0;
+    auto kern = scan_fwd_kernel<in_t, out_t, T, NW, SB>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    const int64_t grid = p.batch * p.ngroups * tiles;
+    kern<<<(unsigned)grid, NW * kWarp, smem, stream>>>(p, tiles, fl);
+    return (int)cudaGetLastError();
+}
+
+}  // namespace ss2d
+
+extern "C" int ss2d_selective_scan_fwd(const ss2d_scan_fwd_params *pp, void *stream) {
+    if (!pp) return SS2D_EINVAL;
+    const ss2d_scan_fwd_params &p = *pp;
+    if (!p.u || !p.delta || !p.A || !p.B || !p.C) return SS2D_EINVAL;  // out == NULL: states-only sweep (x / ckpt)
+    if (p.batch <= 0 || p.dim <= 0 || p.seqlen <= 0 || p.dstate <= 0 || p.ngroups <= 0) return SS2D_EINVAL;
+    if (p.dim % p.ngroups != 0 || p.dstate > SS2D_MAX_DSTATE) return SS2D_EINVAL;
+    if (p.z && !p.out_z) return SS2D_EINVAL;
+    if (p.batch * p.ngroups * ((p.dim / p.ngroups + 7) / 8) > 0x7fffffffLL) return SS2D_EINVAL;
+    if (p.out_dtype != SS2D_F32 && p.out_dtype != p.in_dtype) return SS2D_EDTYPE;
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    using namespace ss2d;
+    switch (p.in_dtype) {
+        case SS2D_F32: return launch_fwd<float, float>(p, s);
+        case SS2D_F16:
+            return p.out_dtype == SS2D_F32 ? launch_fwd<__half, float>(p, s) : launch_fwd<__half, __half>(p, s);
+        case SS2D_BF16:
+            return p.out_dtype == SS2D_F32 ? launch_fwd<__nv_bfloat16, float>(p, s)
+                                           : launch_fwd<__nv_bfloat16, __nv_bfloat16>(p, s);
+        default: return SS2D_EDTYPE;
+    }
+}

@@ -1,0 +1,162 @@
+/*
+ * ss2d_b200.h — C ABI of libss2d_b200.so: the B200-native (sm_100a) SS2D hot path.
+ *
+ * Every entry point is `extern "C"`, takes plain pointers / sizes / strides and a cudaStream_t passed
+ * as void*, launches asynchronously on that stream and returns 0 on success, a negative SS2D_E* code
+ * for a rejected argument (nothing launched) or a positive cudaError_t.  No torch types, no global
+ * state; all buffers are DEVICE pointers owned by the caller (the torch shim allocates them).
+ *
+ * Each entry point replaces one reference interface (paths relative to the c95yang/FocalNet tree):
+ *
+ *   ss2d_selective_scan_fwd   selective_scan_fwd  kernels/selective_scan/csrc/selective_scan/cusoflex/
+ *                             selective_scan_oflex.cpp:157-243 (pybind `fwd`, :361) and the "core" twin
+ *                             cus/selective_scan.cpp (out dtype == input dtype)
+ *   ss2d_selective_scan_bwd   selective_scan_bwd  selective_scan_oflex.cpp:245-358 (pybind `bwd`, :362)
+ *   ss2d_cross_scan           CrossScanTriton.forward / CrossMergeTriton.backward  ITS/models/csm_triton.py:163-175,202-210
+ *   ss2d_cross_merge          CrossMergeTriton.forward / CrossScanTriton.backward  ITS/models/csm_triton.py:188-200,177-185
+ *   ss2d_cross_scan_fwd/_bwd  (fused) CrossScan -> selective scan -> CrossMerge, i.e. the body of
+ *                             cross_selective_scan  ITS/models/vmamba_layers.py:261-291 without the 4x copies
+ *   ss2d_dwconv_silu_fwd/_bwd permute + depthwise 3x3 conv + bias + SiLU  ITS/models/vmamba_layers.py:460-469,591-594
+ *
+ * Struct fields mirror SSMParamsBase / SSMParamsBwd (csrc/selective_scan/selective_scan.h:26-90) with
+ * 64-bit strides (the reference's uint32 strides overflow past 4.29 G elements).  Strides are in ELEMENTS.
+ */
+#ifndef SS2D_B200_H_
+#define SS2D_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SS2D_ABI_VERSION 1
+
+/* element types of u / delta / B / C / z (in_dtype) and of out / dout (out_dtype) */
+enum { SS2D_F32 = 0, SS2D_F16 = 1, SS2D_BF16 = 2 };
+
+/* negative return codes (argument validation, nothing was launched) */
+enum {
+    SS2D_OK = 0,
+    SS2D_EINVAL = -22,      /* null pointer / bad size / dim % ngroups != 0 / dstate > 256          */
+    SS2D_EDTYPE = -2,       /* unsupported dtype combination (out must be F32 or == in)              */
+    SS2D_ESTRIDE = -3,      /* a last-dimension stride != 1 (selective_scan_oflex.cpp:181-182,198)   */
+    SS2D_EDEVICE = -4       /* no sm_100 device / kernel image missing                               */
+};
+
+#define SS2D_MAX_DSTATE 256 /* selective_scan_oflex.cpp:192 */
+#define SS2D_REF_CHUNK 2048 /* selective_scan_oflex.cpp:218: x has ceil(L/2048) checkpoints          */
+#define SS2D_CKPT_STEPS 256 /* granularity of this library's own fine checkpoints (see `ckpt`)       */
+
+/* ---------------------------------------------------------------------------------------------
+ * selective scan, scan-order operands (seam S1)
+ *   u, delta : (batch, dim, seqlen)   in_dtype, last stride 1
+ *   A        : (dim, dstate)          f32 contiguous
+ *   B, C     : (batch, ngroups, dstate, seqlen) in_dtype, last stride 1
+ *   D, delta_bias : (dim) f32 or NULL ; z : (batch, dim, seqlen) in_dtype or NULL
+ *   out      : (batch, dim, seqlen)   out_dtype, contiguous rows (stride given)
+ *   x        : (batch, dim, ceil(seqlen/2048), 2*dstate) f32 contiguous — (running prod a, h) at the
+ *              end of every 2048-step chunk, exactly the reference's checkpoint tensor; may be NULL
+ *   ckpt     : (batch, dim, ceil(seqlen/256), dstate) f32 contiguous or NULL — h at the END of every
+ *              256-step chunk; the backward recomputes chunk interiors from it
+ *   out_z    : (batch, dim, seqlen) out_dtype, only with z: out_z = out * silu(z) (out stays un-gated)
+ * ------------------------------------------------------------------------------------------- */
+typedef struct ss2d_scan_fwd_params {
+    int64_t batch, dim, seqlen, dstate, ngroups;
+    int32_t in_dtype, out_dtype, delta_softplus, reserved0;
+    const void *u, *delta;
+    const float *A;
+    const void *B, *C;
+    const float *D, *delta_bias;
+    const void *z;
+    int64_t u_bstride, u_dstride, delta_bstride, delta_dstride;
+    int64_t B_bstride, B_gstride, B_nstride, C_bstride, C_gstride, C_nstride;
+    int64_t z_bstride, z_dstride;
+    void *out;
+    int64_t out_bstride, out_dstride;
+    void *out_z;
+    float *x;
+    float *ckpt;
+} ss2d_scan_fwd_params;
+
+/*   dout     : (batch, dim, seqlen) out_dtype, last stride 1
+ *   ckpt     : fine checkpoints written by the forward, or NULL together with x == the reference
+ *              tensor (then the library rebuilds the fine checkpoints in `ckpt_scratch` first)
+ *   du, ddelta : (batch, dim, seqlen) in_dtype contiguous ; dz likewise (only with z; needs out)
+ *   dA (dim,dstate), dD, ddelta_bias (dim) : f32, MUST BE ZEROED by the caller (accumulated over batch)
+ *   dB, dC   : (batch, ngroups, dstate, seqlen) f32 contiguous, MUST BE ZEROED (accumulated over the
+ *              channels of a group); the shim casts them to in_dtype afterwards (oflex.cpp:356)     */
+typedef struct ss2d_scan_bwd_params {
+    ss2d_scan_fwd_params f; /* the forward operands (out/out_z unused unless z != NULL: then f.out = un-gated out) */
+    const void *dout;
+    int64_t dout_bstride, dout_dstride;
+    float *ckpt_scratch; /* (batch, dim, ceil(seqlen/256), dstate) f32, required when f.ckpt == NULL and seqlen > 256 */
+    void *du, *ddelta, *dz;
+    float *dA, *dB, *dC, *dD, *ddelta_bias;
+} ss2d_scan_bwd_params;
+
+int ss2d_abi_version(void);
+/* "sm_100a" build tag + kernel variant list; static string */
+const char *ss2d_build_info(void);
+/* human-readable text for a return code of this library (negative) or of CUDA (positive) */
+const char *ss2d_error_string(int code);
+
+int ss2d_selective_scan_fwd(const ss2d_scan_fwd_params *p, void *stream);
+int ss2d_selective_scan_bwd(const ss2d_scan_bwd_params *p, void *stream);
+
+/* x:(B,C,H,W) -> xs:(B,4,C,H*W); dtype as enum above; both contiguous */
+int ss2d_cross_scan(const void *x, void *xs, int64_t B, int64_t C, int64_t H, int64_t W, int32_t dtype, void *stream);
+/* ys:(B,4,C,H*W) -> y:(B,C,H*W) (spatial order), sum of the four un-permuted directions */
+int ss2d_cross_merge(const void *ys, void *y, int64_t B, int64_t C, int64_t H, int64_t W, int32_t dtype, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * fused SS2D core (seam S3): operands in SPATIAL order, the four scan directions are applied in the
+ * kernel's load / store addressing — no (B,4,D,L) copy of x or of y is ever materialised.
+ *   x      : (batch, D, H, W)            in_dtype, contiguous           (u of all four directions)
+ *   delta  : (batch, 4, D, H*W)          in_dtype, spatial order l=h*W+w (dt_proj output, pre-softplus)
+ *   B, C   : (batch, 4, dstate, H*W)     in_dtype, spatial order
+ *   A (4*D,dstate), Dskip (4*D), delta_bias (4*D) : f32, channel index k*D+d (vmamba_layers.py:273-279)
+ *   y      : (batch, D, H*W) f32, spatial order, = CrossMerge of the four scans; MUST BE ZEROED (directions
+ *            are accumulated with red.global.add.f32)
+ *   ckpt   : (batch, 4*D, ceil(L/256), dstate) f32 or NULL
+ * ------------------------------------------------------------------------------------------- */
+typedef struct ss2d_cross_fwd_params {
+    int64_t batch, D, H, W, dstate;
+    int32_t in_dtype, delta_softplus;
+    const void *x, *delta, *B, *C;
+    const float *A, *Dskip, *delta_bias;
+    float *y;
+    float *ckpt;
+} ss2d_cross_fwd_params;
+
+/*   dy : (batch, D, H*W) f32 spatial.  dx (batch,D,H*W) f32 ZEROED; ddelta (batch,4,D,H*W) in_dtype;
+ *   dB, dC (batch,4,dstate,H*W) f32 ZEROED; dA (4*D,dstate), dDskip, ddelta_bias (4*D) f32 ZEROED.      */
+typedef struct ss2d_cross_bwd_params {
+    ss2d_cross_fwd_params f;
+    const float *dy;
+    float *ckpt_scratch;
+    float *dx;
+    void *ddelta;
+    float *dA, *dB, *dC, *dDskip, *ddelta_bias;
+} ss2d_cross_bwd_params;
+
+int ss2d_cross_scan_fwd(const ss2d_cross_fwd_params *p, void *stream);
+int ss2d_cross_scan_bwd(const ss2d_cross_bwd_params *p, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * depthwise 3x3 conv (pad 1) + bias + SiLU reading channels-last, writing channels-first.
+ *   xin  : (batch, H, W, cstride) f32 — first C channels of every pixel are convolved (the in_proj
+ *          output keeps x | z interleaved per pixel, vmamba_layers.py:585-587)
+ *   weight (C,3,3), bias (C) or NULL : f32 ;  out : (batch, C, H, W) f32
+ * bwd: dout (batch,C,H,W) -> dxin (batch,H,W,dx_cstride) first C channels written; dweight (C,9), dbias (C) ZEROED
+ * ------------------------------------------------------------------------------------------- */
+int ss2d_dwconv_silu_fwd(const float *xin, int64_t cstride, const float *weight, const float *bias, float *out,
+                         int64_t batch, int64_t C, int64_t H, int64_t W, void *stream);
+int ss2d_dwconv_silu_bwd(const float *xin, int64_t cstride, const float *weight, const float *bias, const float *dout,
+                         float *dxin, int64_t dx_cstride, float *dweight, float *dbias, int64_t batch, int64_t C,
+                         int64_t H, int64_t W, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SS2D_B200_H_ */

@@ -1,0 +1,132 @@
+// pipe_bench.cu — measures the per-SM issue rates the scan kernels are bounded by on this B200:
+// MUFU.EX2, FFMA, FFMA+MUFU mix, SHFL, LDS.128, and global RED.ADD.F32 (scalar / v4).
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o pipe_bench pipe_bench.cu ; run on the GPU box.
+#include <cstdio>
+#include <cuda_runtime.h>
+
+#define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %d\n", cudaGetErrorString(e), __LINE__); return 1; } } while (0)
+
+__device__ __forceinline__ float ex2(float x) { float y; asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+constexpr int ITERS = 2048;
+constexpr int ILP = 8;
+
+__global__ void k_mufu(float *out, float seed) {
+    float v[ILP];
+#pragma unroll
+    for (int i = 0; i < ILP; ++i) v[i] = seed + i * 1e-3f + threadIdx.x * 1e-6f;
+    for (int it = 0; it < ITERS; ++it) {
+#pragma unroll
+        for (int i = 0; i < ILP; ++i) v[i] = ex2(v[i]);
+    }
+    float s = 0; for (int i = 0; i < ILP; ++i) s += v[i];
+    if (s == 123.456f) out[0] = s;
+}
+__global__ void k_ffma(float *out, float seed) {
+    float v[ILP]; float a = seed, b = seed * 0.5f;
+#pragma unroll
+    for (int i = 0; i < ILP; ++i) v[i] = seed + i;
+    for (int it = 0; it < ITERS; ++it) {
+#pragma unroll
+        for (int i = 0; i < ILP; ++i) v[i] = fmaf(v[i], a, b);
+    }
+    float s = 0; for (int i = 0; i < ILP; ++i) s += v[i];
+    if (s == 123.456f) out[0] = s;
+}
+// R FFMA per MUFU, independent chains
+template <int R> __global__ void k_mix(float *out, float seed) {
+    float v[ILP], w[ILP]; float a = seed, b = seed * 0.5f;
+#pragma unroll
+    for (int i = 0; i < ILP; ++i) { v[i] = seed + i; w[i] = seed * 0.1f + i * 1e-3f; }
+    for (int it = 0; it < ITERS; ++it) {
+#pragma unroll
+        for (int i = 0; i < ILP; ++i) {
+            w[i] = ex2(w[i]);
+#pragma unroll
+            for (int r = 0; r < R; ++r) v[i] = fmaf(v[i], a, b);
+        }
+    }
+    float s = 0; for (int i = 0; i < ILP; ++i) s += v[i] + w[i];
+    if (s == 123.456f) out[0] = s;
+}
+__global__ void k_shfl(float *out, float seed) {
+    float v[ILP];
+#pragma unroll
+    for (int i = 0; i < ILP; ++i) v[i] = seed + i + threadIdx.x;
+    for (int it = 0; it < ITERS; ++it) {
+#pragma unroll
+        for (int i = 0; i < ILP; ++i) v[i] = __shfl_up_sync(0xffffffffu, v[i], 1);
+    }
+    float s = 0; for (int i = 0; i < ILP; ++i) s += v[i];
+    if (s == 123.456f) out[0] = s;
+}
+__global__ void k_lds128(float *out, float seed) {
+    __shared__ float4 sm[1024];
+    for (int i = threadIdx.x; i < 1024; i += blockDim.x) sm[i] = make_float4(seed, seed, seed, seed);
+    __syncthreads();
+    float4 acc = make_float4(0, 0, 0, 0);
+    int idx = threadIdx.x;
+    for (int it = 0; it < ITERS; ++it) {
+#pragma unroll
+        for (int i = 0; i < ILP; ++i) { float4 t = sm[(idx + i * 32) & 1023]; acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w; }
+        idx += 1;
+    }
+    if (acc.x + acc.y + acc.z + acc.w == 123.456f) out[0] = acc.x;
+}
+// global reductions: every thread adds into its own float (spread, coalesced per warp), repeated over a window
+__global__ void k_red(float *buf, size_t n, int reps) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (int r = 0; r < reps; ++r) {
+        size_t j = (i + (size_t)r * 977 * 32) % n;
+        asm volatile("red.global.add.f32 [%0], %1;" ::"l"(buf + j), "f"(1.0f) : "memory");
+    }
+}
+__global__ void k_red4(float *buf, size_t n4, int reps) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (int r = 0; r < reps; ++r) {
+        size_t j = (i + (size_t)r * 977 * 32) % n4;
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %1, %1, %1};" ::"l"(buf + 4 * j), "f"(1.0f) : "memory");
+    }
+}
+
+template <typename F> float time_ms(F f, int n = 5) {
+    cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
+    f(); cudaDeviceSynchronize();
+    float best = 1e30f;
+    for (int i = 0; i < n; ++i) { cudaEventRecord(a); f(); cudaEventRecord(b); cudaEventSynchronize(b); float ms; cudaEventElapsedTime(&ms, a, b); best = ms < best ? ms : best; }
+    return best;
+}
+
+int main() {
+    cudaDeviceProp pr; CK(cudaGetDeviceProperties(&pr, 0));
+    int sms = pr.multiProcessorCount; int clk_khz = 0; cudaDeviceGetAttribute(&clk_khz, cudaDevAttrClockRate, 0);
+    printf("device %s, %d SMs, max clock %d MHz\n", pr.name, sms, clk_khz / 1000);
+    float *out; CK(cudaMalloc(&out, 1 << 20));
+    const int blocks = sms * 8, threads = 256;  // 64 warps/SM
+    const double warp_instrs = (double)blocks * (threads / 32) * ITERS * ILP;
+    auto rep = [&](const char *name, float ms, double instr_mult) {
+        double wi = warp_instrs * instr_mult;
+        double per_sm_per_ns = wi / sms / (ms * 1e6);
+        printf("%-28s %8.3f ms  %7.3f warp-instr/ns/SM  = %6.2f lanes/clk/SM @%d MHz\n", name, ms, per_sm_per_ns,
+               per_sm_per_ns * 32 / (clk_khz / 1e6), clk_khz / 1000);
+    };
+    rep("MUFU.EX2", time_ms([&] { k_mufu<<<blocks, threads>>>(out, 0.5f); }), 1);
+    rep("FFMA (reg,reg,reg)", time_ms([&] { k_ffma<<<blocks, threads>>>(out, 0.5f); }), 1);
+    rep("mix 4 FFMA : 1 MUFU (total)", time_ms([&] { k_mix<4><<<blocks, threads>>>(out, 0.5f); }), 5);
+    rep("mix 6 FFMA : 1 MUFU (total)", time_ms([&] { k_mix<6><<<blocks, threads>>>(out, 0.5f); }), 7);
+    rep("mix 8 FFMA : 1 MUFU (total)", time_ms([&] { k_mix<8><<<blocks, threads>>>(out, 0.5f); }), 9);
+    rep("SHFL.UP", time_ms([&] { k_shfl<<<blocks, threads>>>(out, 0.5f); }), 1);
+    rep("LDS.128 (conflict-free)", time_ms([&] { k_lds128<<<blocks, threads>>>(out, 0.5f); }), 1);
+    // reductions: 64 MB window (fits L2), 16 M threads x reps
+    size_t n = 16u << 20; float *buf; CK(cudaMalloc(&buf, n * 4)); CK(cudaMemset(buf, 0, n * 4));
+    for (int reps : {1, 8}) {
+        int rb = 4096 * 4, rt = 256; double ops = (double)rb * rt * reps;
+        float ms = time_ms([&] { k_red<<<rb, rt>>>(buf, n, reps); });
+        printf("RED.ADD.F32 spread  reps=%d  %8.3f ms  %7.2f G red/s  (%6.1f GB/s payload)\n", reps, ms, ops / ms / 1e6, ops * 4 / ms / 1e6);
+        ms = time_ms([&] { k_red4<<<rb, rt>>>(buf, n / 4, reps); });
+        printf("RED.ADD.V4.F32      reps=%d  %8.3f ms  %7.2f G red/s  (%6.1f GB/s payload)\n", reps, ms, ops / ms / 1e6, ops * 16 / ms / 1e6);
+    }
+    CK(cudaDeviceSynchronize());
+    printf("done\n");
+    return 0;
+}
