@@ -1,0 +1,301 @@
+#!/usr/bin/env python
+"""bench.py — SS2D selective-scan microbench (BASELINE.json configs[1]) on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--dtype fp32|bf16] [--impl ours|reference]
+
+Workload ("ss2d_scan_micro"): B=8, D=192 x K=4 directions (dim 768), N=16, L=64*64, delta_softplus, D and delta_bias
+present — the reference test's input distributions (test_selective_scan.py:406-441) at the model's shapes.  One
+STEP = selective-scan forward + backward over one batch (seam S1, `selective_scan_cuda_oflex.fwd/.bwd`).
+`value` = ALGORITHMIC bytes of fwd+bwd (SURVEY §8d "Level A": 858.9 MB fp32) x steps x ranks / time, in GB/s; the
+inputs (0.4 GB > 126 MB L2) are resident in HBM and larger than L2, so no explicit flush is needed.
+N > 1: the batch axis shards with no data-path collective (weak scaling, 8 images' sequences per GPU).
+
+`--impl reference`: the reference's CPU path (selective_scan_ref, restated in oracle/ss2d_oracle.py as a torch
+port) on the host cores, on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORK = dict(batch=8, dim=768, dstate=16, seqlen=4096, ngroups=4)
+
+
+def algorithmic_bytes(B, Dm, N, L, G, s_in, s_out):
+    """SURVEY §8(d), Level A.  fwd: read u,delta,B,C, write out (+checkpoints); bwd: read the same + dout, write
+    du, ddelta (input dtype) and dB, dC (fp32)."""
+    big, bc = B * Dm * L, B * G * N * L
+    fwd = s_in * (2 * big + 2 * bc) + s_out * big + 4 * B * Dm * (-(-L // 2048)) * 2 * N
+    bwd = s_in * (2 * big + 2 * bc) + s_out * big + s_in * 2 * big + 4 * 2 * bc
+    return fwd, bwd
+
+
+def make_inputs(device, dtype, seed, batch=None, pin=False):
+    w = dict(WORK)
+    if batch:
+        w["batch"] = batch
+    g = torch.Generator().manual_seed(seed)
+    B, Dm, N, L, G = w["batch"], w["dim"], w["dstate"], w["seqlen"], w["ngroups"]
+    t = dict(
+        A=-0.5 * torch.rand(Dm, N, generator=g),
+        B=torch.randn(B, G, N, L, generator=g).to(dtype),
+        C=torch.randn(B, G, N, L, generator=g).to(dtype),
+        D=torch.randn(Dm, generator=g),
+        delta_bias=0.5 * torch.rand(Dm, generator=g),
+        u=torch.randn(B, Dm, L, generator=g).to(dtype),
+        delta=(0.5 * torch.rand(B, Dm, L, generator=g)).to(dtype),
+        dout=torch.randn(B, Dm, L, generator=g),
+    )
+    if pin:
+        return {k: v.pin_memory() for k, v in t.items()}
+    return {k: v.to(device) for k, v in t.items()}
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop_evt = index, [], threading.Event()
+
+    def run(self):
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
+                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self._stop_evt.wait(0.1)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=6)
+        sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+def cpu_baseline(dtype_name, sample_batch=1, threads=None):
+    """Times the torch port of selective_scan_ref (fwd + autograd bwd) on `sample_batch` of the 8 batch rows."""
+    from oracle.ss2d_oracle import selective_scan_ref_port
+    if threads:
+        torch.set_num_threads(threads)
+    d = make_inputs("cpu", torch.float32, 0, batch=sample_batch)
+    leaves = {k: d[k].clone().requires_grad_() for k in ("u", "delta", "A", "B", "C", "D", "delta_bias")}
+    t0 = time.perf_counter()
+    out = selective_scan_ref_port(leaves["u"], leaves["delta"], leaves["A"], leaves["B"], leaves["C"], leaves["D"], None,
+                                  leaves["delta_bias"], True)
+    out.backward(d["dout"])
+    dt = time.perf_counter() - t0
+    f, b = algorithmic_bytes(sample_batch, WORK["dim"], WORK["dstate"], WORK["seqlen"], WORK["ngroups"], 4, 4)
+    return {"value": (f + b) / dt / 1e9, "unit": "GB/s", "cores": torch.get_num_threads(), "kind": "port",
+            "seconds": dt, "host_cpus": os.cpu_count(),
+            "sample": f"selective_scan_ref (torch port, fp32) fwd+autograd-bwd on batch {sample_batch} of {WORK['batch']} "
+                      f"(dim 768, N 16, L 4096): {(f + b) / 1e6:.1f} MB algorithmic"}
+
+
+def run_reference(args, rank, world):
+    """The reference arm: the reference's own CPU implementation of the path on the host cores."""
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 3))
+    best = None
+    for _ in range(min(args.warmup, 1)):
+        cpu_baseline(args.dtype)
+    for _ in range(steps):
+        r = cpu_baseline(args.dtype)
+        best = r if best is None or r["value"] > best["value"] else best
+    f, b = algorithmic_bytes(1, WORK["dim"], WORK["dstate"], WORK["seqlen"], WORK["ngroups"], 4, 4)
+    line = {"impl": "reference", "metric": "ss2d_scan_fwd_bwd_algorithmic_GBps", "value": best["value"], "unit": "GB/s",
+            "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": best["seconds"] * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "ss2d_scan_micro", **WORK, "sample_batch": 1},
+            "cpu_baseline": {k: best[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": best["value"], "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--dtype", default="fp32", choices=["fp32", "bf16"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch.distributed as dist
+    from focalnet_b200 import _lib, scan_bwd, scan_fwd
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: focalnet_b200 has no CPU path (use --impl reference for the CPU arm)")
+    _lib.lib()  # fail loudly if the CUDA library is missing
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    dtype = torch.float32 if args.dtype == "fp32" else torch.bfloat16
+    d = make_inputs(dev, dtype, seed=rank)
+    fargs = (d["u"], d["delta"], d["A"], d["B"], d["C"], d["D"], d["delta_bias"])
+    launches = [0]
+
+    def step():
+        out, x, ckpt, _ = scan_fwd(*fargs, True, 1, True)
+        g = scan_bwd(*fargs, d["dout"], x, True, 1, ckpt=ckpt)
+        launches[0] += 2
+        return out, g
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches[0] = 0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    n_launch = launches[0]
+    clocks = sampler.stop()
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+
+    s_in = 4 if dtype == torch.float32 else 2
+    fb, bb = algorithmic_bytes(WORK["batch"], WORK["dim"], WORK["dstate"], WORK["seqlen"], WORK["ngroups"], s_in, 4)
+    ms_step = ms / args.steps
+    value = (fb + bb) * world / (ms_step * 1e-3) / 1e9
+
+    # ---- per-kernel durations (CUDA events on the launching stream) for the roofline of the dominant kernel ----
+    def kernel_ms(fn, n):
+        evs = []
+        for _ in range(n):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); fn(); b.record()
+            evs.append((a, b))
+        torch.cuda.synchronize()
+        ts = sorted(a.elapsed_time(b) for a, b in evs)
+        return sum(ts) / len(ts), ts[0]
+
+    out, x, ckpt, _ = scan_fwd(*fargs, True, 1, True)
+    n_k = max(5, min(args.steps, 20))
+    fwd_ms, fwd_best = kernel_ms(lambda: scan_fwd(*fargs, True, 1, True), n_k)
+    bwd_ms, bwd_best = kernel_ms(lambda: scan_bwd(*fargs, d["dout"], x, True, 1, ckpt=ckpt), n_k)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    dom, dom_ms, dom_bytes = ("scan_bwd_kernel", bwd_ms, bb) if bwd_ms >= fwd_ms else ("scan_fwd_kernel", fwd_ms, fb)
+    achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650 (B200_PROFILING.md)",
+                "traffic": None, "algorithmic_bytes": dom_bytes, "avg_kernel_ms": dom_ms,
+                "fwd": {"ms": fwd_ms, "GBps": fb / fwd_ms / 1e6, "frac": fb / fwd_ms / 1e6 / peak},
+                "bwd": {"ms": bwd_ms, "GBps": bb / bwd_ms / 1e6, "frac": bb / bwd_ms / 1e6 / peak},
+                "fwd_bwd_frac": (fb + bb) / (fwd_ms + bwd_ms) / 1e6 / peak,
+                "note": "host launch gap included in each event pair; kernel is FMA-issue/MUFU bound, see DESIGN.md"}
+    traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(traffic_file):
+        try:
+            roofline["traffic"] = json.load(open(traffic_file)).get(f"{dom}_{args.dtype}")
+        except Exception:
+            pass
+
+    # ---- end-to-end through the public API with HOST buffers: H2D of the step's inputs + D2H of its result ----
+    host = make_inputs("cpu", dtype, seed=rank, pin=True)
+    names = ("u", "delta", "A", "B", "C", "D", "delta_bias", "dout")
+    h2d = sum(host[k].numel() * host[k].element_size() for k in names)
+    res_host = torch.empty(WORK["dim"] * (WORK["dstate"] + 2) + 1, dtype=torch.float32).pin_memory()
+
+    def e2e_step():
+        dd = {k: host[k].to(dev, non_blocking=True) for k in names}
+        a = (dd["u"], dd["delta"], dd["A"], dd["B"], dd["C"], dd["D"], dd["delta_bias"])
+        o, xx, ck, _ = scan_fwd(*a, True, 1, True)
+        g = scan_bwd(*a, dd["dout"], xx, True, 1, ckpt=ck)
+        res = torch.cat([g[2].flatten(), g[5], g[6], o.sum().view(1)])  # dA, dD, ddelta_bias, checksum(out)
+        res_host.copy_(res, non_blocking=True)
+
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(e2e_steps):
+        e2e_step()
+    e1.record()
+    barrier()
+    e2e_ms = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3) / e2e_steps
+    if world > 1:
+        t = torch.tensor([e2e_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    e2e = {"value": (fb + bb) * world / (e2e_ms * 1e-3) / 1e9, "unit": "GB/s", "ms_per_step": e2e_ms,
+           "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": res_host.numel() * 4}
+
+    if rank == 0:
+        line = {"metric": "ss2d_scan_fwd_bwd_algorithmic_GBps", "value": value, "unit": "GB/s", "n_gpus": world,
+                "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32" if dtype == torch.float32 else "bf16(in)/f32(state,out)",
+                "data": "synthetic",
+                "config": {"workload": "ss2d_scan_micro", **WORK, "per_gpu_batch": WORK["batch"], "delta_softplus": True,
+                           "l2": "inputs (0.42 GB fp32) larger than the 126 MB L2; no flush", "seam": "S1 fwd+bwd",
+                           "algorithmic_MB": (fb + bb) / 1e6},
+                "hbm_frac": value / world / peak, "roofline": roofline, "e2e": e2e, "gpu_launches": n_launch,
+                "clocks": clocks, "lib": _lib.lib().ss2d_build_info().decode()}
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = {k: v for k, v in cpu_baseline(args.dtype).items() if k != "seconds"}
+            try:
+                from tests._util import load_ref_cuda
+                ref = load_ref_cuda()
+                if ref is not None:
+                    ro, rx = ref.fwd(*fargs, True, 1, True)
+                    rf, _ = kernel_ms(lambda: ref.fwd(*fargs, True, 1, True), 5)
+                    rb, _ = kernel_ms(lambda: ref.bwd(*fargs, d["dout"], rx, True, 1), 5)
+                    line["ref_cuda_sm100a_rebuild"] = {"fwd_ms": rf, "bwd_ms": rb, "GBps": (fb + bb) / (rf + rb) / 1e6,
+                                                       "note": "reference oflex kernels recompiled for sm_100a (oracle/_ref), same tensors"}
+            except Exception as exc:  # comparison leg only
+                line["ref_cuda_sm100a_rebuild"] = {"unavailable": str(exc)[:120]}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

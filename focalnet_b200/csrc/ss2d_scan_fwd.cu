@@ -14,6 +14,8 @@
 #include "ss2d_common.cuh"
 #include "ss2d_scan_tile.cuh"
 #include "../../include/ss2d_b200.h"
+#include <cstdlib>
+#include <cstring>
 
 namespace ss2d {
 
@@ -21,41 +23,172 @@ struct FwdFlags {
     bool vec_u, vec_delta, vec_bc, vec_out, vec_z;
 };
 
-// One state of one chunk for this lane's T steps.  `FIRST`/`n` index the carry arrays.
+// BATCH states of one chunk for this lane's T steps, processed together so that the BATCH warp scans
+// (5 dependent shuffle rounds each) are in flight at the same time — the scan's shuffle latency is what
+// bounds this kernel, not its instruction count.
 //   pass 1 keeps the running product and the local state of every step (Pcum_i, hloc_i) in the registers
 //   that held a_i and b_i, so pass 2 (h_i = Pcum_i * h_in + hloc_i) has no serial dependency.
-template <typename in_t, int T, int SLOTS>
-__device__ __forceinline__ void fwd_one_state(const unsigned char *Brow, const unsigned char *Crow, int lane,
-                                              const float (&dl)[T], const float (&du)[T], float (&y)[T], float A2,
-                                              float *ck /* [SLOTS] strided by ck_stride */, int ck_stride, float *sP) {
-    float a[T], hl[T];
-    {
-        float Bv[T];
-        lds_block<in_t, T>(Brow, lane, Bv);
+#ifndef SS2D_KNOCK
+#define SS2D_KNOCK 0  // diagnosis only: 1 = no shuffles, 2 = no MUFU, 3 = no B/C LDS, 4 = no pass-1/2 chains
+#endif
+template <typename in_t, int T, int SLOTS, int BATCH>
+__device__ __forceinline__ void fwd_states(const unsigned char *Brow, const unsigned char *Crow, int lane,
+                                           const float (&dl)[T], const float (&du)[T], float (&y)[T],
+                                           const float *sA2, float *ck /* [SLOTS] strided by ck_stride */,
+                                           int ck_stride, float *sP) {
+    using RL = RowLayout<in_t, T>;
+    float a[BATCH][T], hl[BATCH][T];
 #pragma unroll
-        for (int i = 0; i < T; ++i) { a[i] = ex2(dl[i] * A2); hl[i] = du[i] * Bv[i]; }
+    for (int s = 0; s < BATCH; ++s) {
+        float Bv[T];
+#if SS2D_KNOCK == 3 || SS2D_KNOCK == 8
+#pragma unroll
+        for (int i = 0; i < T; ++i) Bv[i] = dl[i] + s;
+#else
+        lds_block<in_t, T>(Brow + s * RL::row_bytes, lane, Bv);
+#endif
+        const float A2 = sA2[s];
+#pragma unroll
+        for (int i = 0; i < T; ++i) {
+#if SS2D_KNOCK == 2 || SS2D_KNOCK == 8
+            a[s][i] = fmaf(dl[i], A2, 1.f);
+#else
+            a[s][i] = ex2(dl[i] * A2);
+#endif
+            hl[s][i] = du[i] * Bv[i];
+        }
     }
 #pragma unroll
-    for (int i = 1; i < T; ++i) { hl[i] = fmaf(a[i], hl[i - 1], hl[i]); a[i] *= a[i - 1]; }
-    float P = a[T - 1], H = hl[T - 1];
-    warp_scan_inclusive(P, H, lane);
-    float Pe = __shfl_up_sync(0xffffffffu, P, 1), He = __shfl_up_sync(0xffffffffu, H, 1);
-    if (lane == 0) { Pe = 1.f; He = 0.f; }
-    const float carry = ck[(SLOTS - 1) * ck_stride];  // h at the end of the previous chunk
-    const float hin = fmaf(Pe, carry, He);
-    float Cv[T];
-    lds_block<in_t, T>(Crow, lane, Cv);
-    float h = hin;
+    for (int i = 1; i < T; ++i) {
 #pragma unroll
-    for (int i = 0; i < T; ++i) { h = fmaf(a[i], hin, hl[i]); y[i] = fmaf(Cv[i], h, y[i]); }
-    // lanes whose block ends on a checkpoint boundary publish h there (the last slot is the chunk carry)
+        for (int s = 0; s < BATCH; ++s) { hl[s][i] = fmaf(a[s][i], hl[s][i - 1], hl[s][i]); a[s][i] *= a[s][i - 1]; }
+    }
+    float P[BATCH], H[BATCH];
+#pragma unroll
+    for (int s = 0; s < BATCH; ++s) { P[s] = a[s][T - 1]; H[s] = hl[s][T - 1]; }
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        float Pp[BATCH], Hp[BATCH];
+#pragma unroll
+        for (int s = 0; s < BATCH; ++s) {
+#if SS2D_KNOCK == 1 || SS2D_KNOCK == 8
+            Pp[s] = P[s] * 0.5f; Hp[s] = H[s] + 1.f;
+#else
+            Pp[s] = __shfl_up_sync(0xffffffffu, P[s], d);
+            Hp[s] = __shfl_up_sync(0xffffffffu, H[s], d);
+#endif
+        }
+        if (lane >= d) {
+#pragma unroll
+            for (int s = 0; s < BATCH; ++s) { H[s] = fmaf(P[s], Hp[s], H[s]); P[s] *= Pp[s]; }
+        }
+    }
+    float hin[BATCH];
+#pragma unroll
+    for (int s = 0; s < BATCH; ++s) {
+        float Pe = __shfl_up_sync(0xffffffffu, P[s], 1), He = __shfl_up_sync(0xffffffffu, H[s], 1);
+        if (lane == 0) { Pe = 1.f; He = 0.f; }
+        hin[s] = fmaf(Pe, ck[(SLOTS - 1) * ck_stride + s], He);  // carry = h at the end of the previous chunk
+    }
     constexpr int lanes_per_slot = kWarp / SLOTS;
-    if ((lane + 1) % lanes_per_slot == 0) ck[((lane + 1) / lanes_per_slot - 1) * ck_stride] = h;
-    if (lane == kWarp - 1) *sP *= P;
+#pragma unroll
+    for (int s = 0; s < BATCH; ++s) {
+        float Cv[T];
+#if SS2D_KNOCK == 3 || SS2D_KNOCK == 8
+#pragma unroll
+        for (int i = 0; i < T; ++i) Cv[i] = du[i] + s;
+#else
+        lds_block<in_t, T>(Crow + s * RL::row_bytes, lane, Cv);
+#endif
+        float h = hin[s];
+#pragma unroll
+        for (int i = 0; i < T; ++i) { h = fmaf(a[s][i], hin[s], hl[s][i]); y[i] = fmaf(Cv[i], h, y[i]); }
+        // lanes whose block ends on a checkpoint boundary publish h there (the last slot is the chunk carry)
+        if ((lane + 1) % lanes_per_slot == 0) ck[((lane + 1) / lanes_per_slot - 1) * ck_stride + s] = h;
+        if (lane == kWarp - 1) sP[s] *= P[s];
+    }
 }
 
-template <typename in_t, typename out_t, int T, int NW, int SB>
-__global__ void __launch_bounds__(NW * kWarp, 2)
+// ---- software-pipelined state block --------------------------------------------------------------------
+// The warp scan of state r (5 dependent shuffle rounds, ~200 cycles of pure latency) is interleaved, in
+// program order, with the exp / pass-1 work of state r+1, so a warp always has independent instructions
+// to issue while its shuffles are in flight.  (The warps of a CTA run in lock-step between barriers, so
+// leaving the overlap to other warps does not work: they all sit in the same shuffle round.)
+template <typename in_t, int T> struct StatePrep {
+    float a[T], hl[T];  // after pass 1: running product of a / local state at every step
+    // slice 0..4 of the preparation of one state; each slice is independent of the scan in flight
+    template <int SLICE>
+    __device__ __forceinline__ void run(const unsigned char *Brow, int lane, const float (&dl)[T], const float (&du)[T],
+                                        float A2) {
+        constexpr int H1 = T / 2;
+        if constexpr (SLICE == 0 || SLICE == 1) {  // exps and drive terms, half the block each
+            constexpr int lo = SLICE * H1;
+            float Bv[H1];
+            using RL = RowLayout<in_t, T>;
+            const uint4 *src = reinterpret_cast<const uint4 *>(Brow) + RL::lane_unit(lane) + lo / RL::per;
+#pragma unroll
+            for (int i = 0; i < H1 / RL::per; ++i) unpack16<in_t>(src[i], &Bv[i * RL::per]);
+#pragma unroll
+            for (int i = 0; i < H1; ++i) { a[lo + i] = ex2(dl[lo + i] * A2); hl[lo + i] = du[lo + i] * Bv[i]; }
+        } else {  // pass 1 in three slices
+            constexpr int third = (T - 1 + 2) / 3;
+            constexpr int lo = 1 + (SLICE - 2) * third, hi = (lo + third < T) ? lo + third : T;
+#pragma unroll
+            for (int i = lo; i < hi; ++i) { hl[i] = fmaf(a[i], hl[i - 1], hl[i]); a[i] *= a[i - 1]; }
+        }
+    }
+};
+
+template <typename in_t, int T, int SLOTS, int SB>
+__device__ __forceinline__ void fwd_block_pipelined(const unsigned char *buf, int lane, const float (&dl)[T],
+                                                    const float (&du)[T], float (&y)[T], const float *sA2, float *ck,
+                                                    int ck_stride, float *sP) {
+    using RL = RowLayout<in_t, T>;
+    static_assert(T % (2 * RL::per) == 0, "half a lane block must be whole 16-byte pieces");
+    StatePrep<in_t, T> st[2];
+    {
+        const float A2 = sA2[0];
+        st[0].template run<0>(buf, lane, dl, du, A2);
+        st[0].template run<1>(buf, lane, dl, du, A2);
+        st[0].template run<2>(buf, lane, dl, du, A2);
+        st[0].template run<3>(buf, lane, dl, du, A2);
+        st[0].template run<4>(buf, lane, dl, du, A2);
+    }
+    constexpr int lanes_per_slot = kWarp / SLOTS;
+#pragma unroll
+    for (int r = 0; r < SB; ++r) {
+        StatePrep<in_t, T> &cur = st[r & 1], &nxt = st[(r + 1) & 1];
+        const unsigned char *Bnext = buf + (r + 1) * RL::row_bytes;
+        const float A2n = r + 1 < SB ? sA2[r + 1] : 0.f;
+        float P = cur.a[T - 1], H = cur.hl[T - 1];
+#define SS2D_SCAN_STAGE(D, SLICE)                                                   \
+        {                                                                           \
+            const float Pp = __shfl_up_sync(0xffffffffu, P, D);                     \
+            const float Hp = __shfl_up_sync(0xffffffffu, H, D);                     \
+            if (r + 1 < SB) nxt.template run<SLICE>(Bnext, lane, dl, du, A2n);      \
+            if (lane >= D) { H = fmaf(P, Hp, H); P *= Pp; }                         \
+        }
+        SS2D_SCAN_STAGE(1, 0)
+        SS2D_SCAN_STAGE(2, 1)
+        SS2D_SCAN_STAGE(4, 2)
+        SS2D_SCAN_STAGE(8, 3)
+        SS2D_SCAN_STAGE(16, 4)
+#undef SS2D_SCAN_STAGE
+        float Pe = __shfl_up_sync(0xffffffffu, P, 1), He = __shfl_up_sync(0xffffffffu, H, 1);
+        float Cv[T];
+        lds_block<in_t, T>(buf + (SB + r) * RL::row_bytes, lane, Cv);
+        if (lane == 0) { Pe = 1.f; He = 0.f; }
+        const float hin = fmaf(Pe, ck[(SLOTS - 1) * ck_stride + r], He);
+        float h = hin;
+#pragma unroll
+        for (int i = 0; i < T; ++i) { h = fmaf(cur.a[i], hin, cur.hl[i]); y[i] = fmaf(Cv[i], h, y[i]); }
+        if ((lane + 1) % lanes_per_slot == 0) ck[((lane + 1) / lanes_per_slot - 1) * ck_stride + r] = h;
+        if (lane == kWarp - 1) sP[r] *= P;
+    }
+}
+
+template <typename in_t, typename out_t, int T, int NW, int SB, int BATCH, int MINB>
+__global__ void __launch_bounds__(NW * kWarp, MINB)
 scan_fwd_kernel(const ss2d_scan_fwd_params p, const int tiles_per_group, const FwdFlags fl) {
     using FT = BCTile<in_t, T, SB>;
     using RL = typename FT::RL;
@@ -123,8 +256,13 @@ scan_fwd_kernel(const ss2d_scan_fwd_params p, const int tiles_per_group, const F
         const int valid = (int)min((int64_t)T, L - tl);   // may be <= 0
         if (sb == 0) {
             float uv[T];
+#if SS2D_KNOCK == 6
+#pragma unroll
+            for (int i = 0; i < T; ++i) { uv[i] = 0.01f * (lane + i); dl[i] = 0.02f * (lane - i) + ci; }
+#else
             load_block<in_t, T>(u_row + tl, uv, valid, fl.vec_u);
             load_block<in_t, T>(d_row + tl, dl, valid, fl.vec_delta);
+#endif
             if (tl + chunk < L) {  // pull the next chunk's u / delta lines into L2 while this chunk computes
                 prefetch_l2(u_row + tl + chunk);
                 prefetch_l2(d_row + tl + chunk);
@@ -140,21 +278,36 @@ scan_fwd_kernel(const ss2d_scan_fwd_params p, const int tiles_per_group, const F
             }
         }
         const unsigned char *buf = tiles + (q & 1) * FT::tile_bytes;
-        if (N - sb * SB >= SB) {
+#if SS2D_KNOCK != 5
+        {
+            const int n_here = min(SB, N - sb * SB);
+            int r = 0;
+            if (n_here == SB && BATCH == 0) {
+                fwd_block_pipelined<in_t, T, SLOTS, SB>(buf, lane, dl, du, y, sA2 + sb * SB, sCk + sb * SB, Npad,
+                                                        sP + sb * SB);
+                r = SB;
+            } else if (n_here == SB) {
+                constexpr int BT = BATCH > 0 ? BATCH : 1;
 #pragma unroll
-            for (int r = 0; r < SB; ++r)
-                fwd_one_state<in_t, T, SLOTS>(buf + r * RL::row_bytes, buf + (SB + r) * RL::row_bytes, lane, dl, du, y,
-                                             sA2[sb * SB + r], sCk + sb * SB + r, Npad, sP + sb * SB + r);
-        } else {
+                for (int rr = 0; rr < SB; rr += BT)
+                    fwd_states<in_t, T, SLOTS, BT>(buf + rr * RL::row_bytes, buf + (SB + rr) * RL::row_bytes, lane, dl,
+                                                      du, y, sA2 + sb * SB + rr, sCk + sb * SB + rr, Npad,
+                                                      sP + sb * SB + rr);
+                r = SB;
+            }
 #pragma unroll 1
-            for (int r = 0; r < N - sb * SB; ++r)
-                fwd_one_state<in_t, T, SLOTS>(buf + r * RL::row_bytes, buf + (SB + r) * RL::row_bytes, lane, dl, du, y,
-                                             sA2[sb * SB + r], sCk + sb * SB + r, Npad, sP + sb * SB + r);
+            for (; r < n_here; ++r)
+                fwd_states<in_t, T, SLOTS, 1>(buf + r * RL::row_bytes, buf + (SB + r) * RL::row_bytes, lane, dl, du, y,
+                                              sA2 + sb * SB + r, sCk + sb * SB + r, Npad, sP + sb * SB + r);
         }
+#endif
         if (sb == n_sb - 1) {  // chunk finished
             __syncwarp();
             if (active) {
                 if (o_row) {
+#if SS2D_KNOCK == 7
+                    if (y[0] == 123.4f)
+#endif
                     store_block<out_t, T>(o_row + tl, y, valid, fl.vec_out);
                     if (z_row) {
                         float zv[T];
@@ -188,9 +341,8 @@ scan_fwd_kernel(const ss2d_scan_fwd_params p, const int tiles_per_group, const F
 
 static inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
-template <typename in_t, typename out_t>
+template <typename in_t, typename out_t, int T = 16, int NW = 8, int BATCH = 1, int MINB = 2, int SB = 8>
 static int launch_fwd(const ss2d_scan_fwd_params &p, cudaStream_t stream) {
-    constexpr int T = 16, NW = 8, SB = 8;
     using FT = BCTile<in_t, T, SB>;
     const int per_g = (int)(p.dim / p.ngroups);
     const int tiles = (per_g + NW - 1) / NW;
@@ -206,7 +358,8 @@ static int launch_fwd(const ss2d_scan_fwd_params &p, cudaStream_t stream) {
     fl.vec_out = aligned16(p.out) && (!p.out_z || aligned16(p.out_z)) && (p.out_bstride * eo) % 16 == 0 &&
                  (p.out_dstride * eo) % 16 == 0;
     fl.vec_z = p.z && aligned16(p.z) && (p.z_bstride * ei) % 16 == 0 && (p.z_dstride * ei) % 16 == 0;
-    auto kern = scan_fwd_kernel<in_t, out_t, T, NW, SB>;
+    static_assert(BATCH == 0 || SB % BATCH == 0, "BATCH must divide the state block (0 = software-pipelined)");
+    auto kern = scan_fwd_kernel<in_t, out_t, T, NW, SB, BATCH, MINB>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     const int64_t grid = p.batch * p.ngroups * tiles;
@@ -223,10 +376,39 @@ extern "C" int ss2d_selective_scan_fwd(const ss2d_scan_fwd_params *pp, void *str
     if (p.batch <= 0 || p.dim <= 0 || p.seqlen <= 0 || p.dstate <= 0 || p.ngroups <= 0) return SS2D_EINVAL;
     if (p.dim % p.ngroups != 0 || p.dstate > SS2D_MAX_DSTATE) return SS2D_EINVAL;
     if (p.z && !p.out_z) return SS2D_EINVAL;
-    if (p.batch * p.ngroups * ((p.dim / p.ngroups + 7) / 8) > 0x7fffffffLL) return SS2D_EINVAL;
+    if (p.batch * p.ngroups * (p.dim / p.ngroups) > 0x7fffffffLL) return SS2D_EINVAL;
     if (p.out_dtype != SS2D_F32 && p.out_dtype != p.in_dtype) return SS2D_EDTYPE;
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     using namespace ss2d;
+#ifdef SS2D_TUNE  // development knob: alternative tilings for fp32, selected by SS2D_FWD_CFG=TxNWxBATCHxMINB
+    if (p.in_dtype == SS2D_F32) {
+        const char *cfg = getenv("SS2D_FWD_CFG");
+        if (cfg) {
+            // T x NW x BATCH x MINB
+            if (!strcmp(cfg, "16x8x1x2")) return launch_fwd<float, float, 16, 8, 1, 2>(p, s);
+            if (!strcmp(cfg, "8x8x1x3")) return launch_fwd<float, float, 8, 8, 1, 3>(p, s);
+            if (!strcmp(cfg, "8x8x2x3")) return launch_fwd<float, float, 8, 8, 2, 3>(p, s);
+            if (!strcmp(cfg, "8x8x2x2")) return launch_fwd<float, float, 8, 8, 2, 2>(p, s);
+            if (!strcmp(cfg, "8x8x4x2")) return launch_fwd<float, float, 8, 8, 4, 2>(p, s);
+            if (!strcmp(cfg, "8x16x2x1")) return launch_fwd<float, float, 8, 16, 2, 1>(p, s);
+            if (!strcmp(cfg, "8x16x4x1")) return launch_fwd<float, float, 8, 16, 4, 1>(p, s);
+            if (!strcmp(cfg, "16x8x2x1")) return launch_fwd<float, float, 16, 8, 2, 1>(p, s);
+            if (!strcmp(cfg, "16x16x1x1")) return launch_fwd<float, float, 16, 16, 1, 1>(p, s);
+            if (!strcmp(cfg, "16x4x1x4s4")) return launch_fwd<float, float, 16, 4, 1, 4, 4>(p, s);
+            if (!strcmp(cfg, "16x8x1x2s4")) return launch_fwd<float, float, 16, 8, 1, 2, 4>(p, s);
+            if (!strcmp(cfg, "16x4x1x2s8")) return launch_fwd<float, float, 16, 4, 1, 2, 8>(p, s);
+            if (!strcmp(cfg, "8x4x1x4s8")) return launch_fwd<float, float, 8, 4, 1, 4, 8>(p, s);
+            if (!strcmp(cfg, "8x4x2x4s8")) return launch_fwd<float, float, 8, 4, 2, 4, 8>(p, s);
+            if (!strcmp(cfg, "8x4x1x6s4")) return launch_fwd<float, float, 8, 4, 1, 6, 4>(p, s);
+            if (!strcmp(cfg, "8x2x1x8s4")) return launch_fwd<float, float, 8, 2, 1, 8, 4>(p, s);
+            if (!strcmp(cfg, "8x8x0x3")) return launch_fwd<float, float, 8, 8, 0, 3>(p, s);
+            if (!strcmp(cfg, "8x8x0x2")) return launch_fwd<float, float, 8, 8, 0, 2>(p, s);
+            if (!strcmp(cfg, "8x16x0x1")) return launch_fwd<float, float, 8, 16, 0, 1>(p, s);
+            if (!strcmp(cfg, "16x8x0x1")) return launch_fwd<float, float, 16, 8, 0, 1>(p, s);
+            if (!strcmp(cfg, "16x8x0x2")) return launch_fwd<float, float, 16, 8, 0, 2>(p, s);
+        }
+    }
+#endif
     switch (p.in_dtype) {
         case SS2D_F32: return launch_fwd<float, float>(p, s);
         case SS2D_F16:

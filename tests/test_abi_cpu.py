@@ -1,0 +1,68 @@
+"""CPU-side checks of the boundary: the C-ABI library loads and exports every symbol include/ss2d_b200.h
+declares, the ctypes structs match the header's layout, and the host mirror rejects bad arguments the way the
+reference's TORCH_CHECKs do — without ever launching a kernel (no GPU here)."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "ss2d_b200.h")
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from focalnet_b200 import _lib, build
+    build.build()
+    return _lib.lib()
+
+
+def test_every_declared_symbol_is_exported(lib):
+    from focalnet_b200 import _lib
+    src = open(HEADER).read()
+    declared = set(re.findall(r"^(?:int|const char \*)\s*(ss2d_\w+)\(", src, flags=re.M))
+    assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.ss2d_abi_version() == 1
+    assert b"sm_100a" in lib.ss2d_build_info()
+    assert b"invalid" in lib.ss2d_error_string(-22)
+
+
+def test_struct_layout_matches_header(lib):
+    """sizeof computed from the header's field list must equal the ctypes mirror (8-byte fields + 4 int32)."""
+    from focalnet_b200 import _lib
+    assert ctypes.sizeof(_lib.ScanFwdParams) == 5 * 8 + 4 * 4 + 8 * 8 + 12 * 8 + 8 + 16 + 8 * 3
+    assert ctypes.sizeof(_lib.ScanBwdParams) == ctypes.sizeof(_lib.ScanFwdParams) + 8 + 16 + 8 + 8 * 8
+    assert ctypes.sizeof(_lib.CrossFwdParams) == 5 * 8 + 2 * 4 + 9 * 8
+    assert ctypes.sizeof(_lib.CrossBwdParams) == ctypes.sizeof(_lib.CrossFwdParams) + 9 * 8
+
+
+def test_argument_validation_without_gpu(lib):
+    from focalnet_b200 import _lib
+    assert lib.ss2d_selective_scan_fwd(None, None) == -22
+    p = _lib.ScanFwdParams()
+    assert lib.ss2d_selective_scan_fwd(ctypes.cast(ctypes.pointer(p), ctypes.c_void_p), None) == -22  # null pointers
+    pb = _lib.ScanBwdParams()
+    assert lib.ss2d_selective_scan_bwd(ctypes.cast(ctypes.pointer(pb), ctypes.c_void_p), None) == -22
+
+
+def test_host_mirror_has_no_cpu_path():
+    from focalnet_b200 import scan_fwd, selective_scan_fn
+    u = torch.randn(1, 4, 8)
+    A = -torch.rand(4, 2)
+    Bm = torch.randn(1, 1, 2, 8)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        scan_fwd(u, u.clone(), A, Bm, Bm.clone())
+    with pytest.raises(RuntimeError):
+        selective_scan_fn(u, u.clone(), A, Bm, Bm.clone())
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    from focalnet_b200 import _lib
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(RuntimeError, match="no CPU or PyTorch fallback"):
+        _lib.lib()
