@@ -40,10 +40,15 @@ def algorithmic_bytes(B, Dm, N, L, G, s_in, s_out):
     return fwd, bwd
 
 
-def make_inputs(device, dtype, seed, batch=None, pin=False):
+SAMPLE = dict(batch=1, dim=96)  # CPU-arm sample: 1 of 8 images, 24 of the 192 channels of each direction (~15-30 s)
+
+
+def make_inputs(device, dtype, seed, batch=None, pin=False, dim=None):
     w = dict(WORK)
     if batch:
         w["batch"] = batch
+    if dim:
+        w["dim"] = dim
     g = torch.Generator().manual_seed(seed)
     B, Dm, N, L, G = w["batch"], w["dim"], w["dstate"], w["seqlen"], w["ngroups"]
     t = dict(
@@ -62,54 +67,80 @@ def make_inputs(device, dtype, seed, batch=None, pin=False):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clock + throttle reasons DURING the timed region (B200_PROFILING.md): NVML polled every ~2 ms, with
+    the recipe's nvidia-smi query as a fallback when pynvml is unavailable."""
 
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    BITS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.rows, self._stop_evt = index, [], threading.Event()
+        self.index, self.sm, self.mx, self.reasons, self._stop_evt = index, [], [], set(), threading.Event()
+        self.h = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and vis.split(",")[index].isdigit() else index
+            self.nv, self.h = pynvml, pynvml.nvmlDeviceGetHandleByIndex(phys)
+        except Exception:
+            self.h = None
+
+    def _poll_nvml(self):
+        nv = self.nv
+        self.sm.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+        self.mx.append(nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM))
+        try:
+            r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+        except Exception:
+            r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+        self.reasons |= {n for n, bit in self.BITS.items() if r & bit}
+
+    def _poll_smi(self):
+        out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
+                              str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+        r = [c.strip() for c in out.split(",")]
+        if len(r) >= 6 and r[0].isdigit():
+            self.sm.append(int(r[0])); self.mx.append(int(r[1]))
+            self.reasons |= {n for n, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                                "sw_power_cap"), r[2:6]) if v.lower().startswith("active")}
 
     def run(self):
         while not self._stop_evt.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
-                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.split(",")])
+                self._poll_nvml() if self.h is not None else self._poll_smi()
             except Exception:
                 pass
-            self._stop_evt.wait(0.1)
+            self._stop_evt.wait(0.002 if self.h is not None else 0.1)
 
     def stop(self):
         self._stop_evt.set()
         self.join(timeout=6)
-        sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
-        mx = [int(r[1]) for r in self.rows if r[1].isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for r in self.rows for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(self.rows)}
+        sm = sorted(self.sm)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(self.mx) if self.mx else None,
+                "reasons": sorted(self.reasons), "samples": len(sm), "source": "nvml" if self.h is not None else "nvidia-smi"}
 
 
-def cpu_baseline(dtype_name, sample_batch=1, threads=None):
-    """Times the torch port of selective_scan_ref (fwd + autograd bwd) on `sample_batch` of the 8 batch rows."""
+def cpu_baseline(dtype_name, sample_batch=SAMPLE["batch"], sample_dim=SAMPLE["dim"], threads=None):
+    """Times the torch port of selective_scan_ref (fwd + autograd bwd) on a bounded sample of the workload:
+    `sample_batch` of the 8 batch rows and `sample_dim` of the 768 channels (all 4 groups, full L = 4096; the
+    reference's autograd backward is O(L^2) in memory traffic, so L is what makes it slow and is kept)."""
     from oracle.ss2d_oracle import selective_scan_ref_port
     if threads:
         torch.set_num_threads(threads)
-    d = make_inputs("cpu", torch.float32, 0, batch=sample_batch)
+    d = make_inputs("cpu", torch.float32, 0, batch=sample_batch, dim=sample_dim)
     leaves = {k: d[k].clone().requires_grad_() for k in ("u", "delta", "A", "B", "C", "D", "delta_bias")}
     t0 = time.perf_counter()
     out = selective_scan_ref_port(leaves["u"], leaves["delta"], leaves["A"], leaves["B"], leaves["C"], leaves["D"], None,
                                   leaves["delta_bias"], True)
     out.backward(d["dout"])
     dt = time.perf_counter() - t0
-    f, b = algorithmic_bytes(sample_batch, WORK["dim"], WORK["dstate"], WORK["seqlen"], WORK["ngroups"], 4, 4)
+    f, b = algorithmic_bytes(sample_batch, sample_dim, WORK["dstate"], WORK["seqlen"], WORK["ngroups"], 4, 4)
     return {"value": (f + b) / dt / 1e9, "unit": "GB/s", "cores": torch.get_num_threads(), "kind": "port",
             "seconds": dt, "host_cpus": os.cpu_count(),
-            "sample": f"selective_scan_ref (torch port, fp32) fwd+autograd-bwd on batch {sample_batch} of {WORK['batch']} "
-                      f"(dim 768, N 16, L 4096): {(f + b) / 1e6:.1f} MB algorithmic"}
+            "sample": f"selective_scan_ref (torch port, fp32) fwd+autograd-bwd on batch {sample_batch} of {WORK['batch']}, "
+                      f"dim {sample_dim} of {WORK['dim']} (4 groups, N 16, L 4096): {(f + b) / 1e6:.1f} MB algorithmic"}
 
 
 def run_reference(args, rank, world):
@@ -123,11 +154,10 @@ def run_reference(args, rank, world):
     for _ in range(steps):
         r = cpu_baseline(args.dtype)
         best = r if best is None or r["value"] > best["value"] else best
-    f, b = algorithmic_bytes(1, WORK["dim"], WORK["dstate"], WORK["seqlen"], WORK["ngroups"], 4, 4)
     line = {"impl": "reference", "metric": "ss2d_scan_fwd_bwd_algorithmic_GBps", "value": best["value"], "unit": "GB/s",
             "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": best["seconds"] * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "ss2d_scan_micro", **WORK, "sample_batch": 1},
+            "config": {"workload": "ss2d_scan_micro", **WORK, "sample_batch": SAMPLE["batch"], "sample_dim": SAMPLE["dim"]},
             "cpu_baseline": {k: best[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": best["value"], "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
