@@ -41,6 +41,7 @@ class CrossFwdParams(C.Structure):
         [(n, _i64) for n in ("batch", "D", "H", "W", "dstate")]
         + [("in_dtype", _i32), ("delta_softplus", _i32)]
         + [(n, _vp) for n in ("x", "delta", "B", "C", "A", "Dskip", "delta_bias", "y", "ckpt")]
+        + [("bc_bstride", _i64), ("bc_gstride", _i64)]
     )
 
 
@@ -73,7 +74,7 @@ def lib():
                                         "ss2d_cross_scan_bwd")}
         sigs.update({n: [_vp, _vp, _i64, _i64, _i64, _i64, _i32, _vp] for n in ("ss2d_cross_scan", "ss2d_cross_merge")})
         sigs["ss2d_dwconv_silu_fwd"] = [_vp, _i64, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _vp]
-        sigs["ss2d_dwconv_silu_bwd"] = [_vp, _i64, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _i64, _i64, _i64, _i64, _vp]
+        sigs["ss2d_dwconv_silu_bwd"] = [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _i64, _i64, _i64, _i64, _vp]
         for name, argtypes in sigs.items():
             fn = getattr(L, name)  # AttributeError here == a symbol of include/ss2d_b200.h is not exported
             fn.restype = C.c_int

@@ -122,6 +122,94 @@ __device__ __forceinline__ void store_block(T *__restrict__ p, const float (&v)[
     }
 }
 
+// ---- CrossScan / CrossMerge folded into the scan's addressing (fused seam S3) -----------------------
+// Direction k maps scan step l to a pixel of the (H, W) plane (vmamba_layers.py:35-37):
+//   k=0: l = h*W+w   k=1: l = w*H+h   k=2: l = L-1-(h*W+w)   k=3: l = L-1-(w*H+h)
+// A lane's T consecutive scan steps are therefore T contiguous pixels (k=0), the same run mirrored (k=2), or a
+// column walk with stride W (k=1,3).  For the column walk, lanes H/T apart sit on adjacent columns, so one
+// warp-wide scalar access still touches whole 32-byte sectors (4 rows x 8 pixels for H=64, T=16).
+struct CrossInfo {
+    int H, W;
+};
+struct CrossWalk {  // pixel offset of scan step l for k in {1,3}, advanced one step at a time
+    int h, w, W, H, dir;
+    __device__ __forceinline__ CrossWalk(int k, int64_t l, int64_t L, int H_, int W_) : W(W_), H(H_) {
+        const int64_t ls = k == 3 ? L - 1 - l : l;  // column-major index w*H + h
+        w = (int)(ls / H_);
+        h = (int)(ls - (int64_t)w * H_);
+        dir = k == 3 ? -1 : 1;
+    }
+    __device__ __forceinline__ int64_t offset() const { return (int64_t)h * W + w; }
+    __device__ __forceinline__ void next() {
+        h += dir;
+        if (h == H) { h = 0; ++w; }
+        if (h < 0) { h = H - 1; --w; }
+    }
+};
+
+// Gather this lane's T scan steps [tl, tl+T) of direction k from a spatial-order plane.
+template <typename T_, int N>
+__device__ __forceinline__ void load_block_cross(const T_ *__restrict__ plane, float (&v)[N], int k, int64_t tl, int64_t L,
+                                                 const CrossInfo &ci, bool vec) {
+    const int valid = (int)min((int64_t)N, L - tl);
+    if (k == 0) {
+        load_block<T_, N>(plane + tl, v, valid, vec);
+    } else if (k == 2) {
+        float t[N];
+        const int64_t start = L - tl - N;  // the mirrored run [start, start+N)
+        if (vec && valid >= N && (start * (int64_t)sizeof(T_)) % 16 == 0) {
+            load_block<T_, N>(plane + start, t, N, true);
+#pragma unroll
+            for (int i = 0; i < N; ++i) v[i] = t[N - 1 - i];
+        } else {
+#pragma unroll
+            for (int i = 0; i < N; ++i) v[i] = i < valid ? to_f32<T_>(plane[L - 1 - (tl + i)]) : 0.f;
+        }
+    } else {
+        CrossWalk cw(k, min(tl, L - 1), L, ci.H, ci.W);
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            v[i] = i < valid ? to_f32<T_>(__ldg(plane + cw.offset())) : 0.f;
+            cw.next();
+        }
+    }
+}
+
+__device__ __forceinline__ void red_add_f32(float *addr, float v) {
+    asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ void red_add_v4(float *addr, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+// Accumulate this lane's T scan steps of direction k into a spatial-order fp32 plane (CrossMerge as a store).
+template <int N>
+__device__ __forceinline__ void red_block_cross(float *__restrict__ plane, const float (&v)[N], int k, int64_t tl, int64_t L,
+                                                const CrossInfo &ci, bool vec) {
+    const int valid = (int)min((int64_t)N, L - tl);
+    if (k == 0 || k == 2) {
+        const int64_t start = k == 0 ? tl : L - tl - N;
+        if (vec && valid >= N && (start & 3) == 0) {
+#pragma unroll
+            for (int i = 0; i < N; i += 4) {
+                if (k == 0) red_add_v4(plane + start + i, v[i], v[i + 1], v[i + 2], v[i + 3]);
+                else red_add_v4(plane + start + i, v[N - 1 - i], v[N - 2 - i], v[N - 3 - i], v[N - 4 - i]);
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < N; ++i)
+                if (i < valid) red_add_f32(plane + (k == 0 ? tl + i : L - 1 - (tl + i)), v[i]);
+        }
+    } else {
+        CrossWalk cw(k, min(tl, L - 1), L, ci.H, ci.W);
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            if (i < valid) red_add_f32(plane + cw.offset(), v[i]);
+            cw.next();
+        }
+    }
+}
+
 // ---- cp.async (LDGSTS) -----------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 // 16-byte async copy, `bytes` (0..16) taken from global, remainder zero-filled

@@ -1,0 +1,135 @@
+// ss2d_cross.cu — stand-alone CrossScan / CrossMerge for sm_100a (seam S2).
+//
+// Replaces the Triton kernels triton_cross_scan / triton_cross_merge (reference: ITS/models/csm_triton.py:7-80)
+// and their torch twins (ITS/models/vmamba_layers.py:29-71).  Scan-order position l of direction k maps to the
+// spatial pixel (vmamba_layers.py:35-37):
+//     k=0: l = h*W + w      k=1: l = w*H + h      k=2: l = L-1-(h*W+w)      k=3: l = L-1-(w*H+h)
+// Pure data movement, HBM-bound: every 32x32 pixel tile of a (b,c) plane goes through shared memory once, so
+// the row-major AND the column-major images are both read/written with full 128-byte coalescing; the flipped
+// directions are the same segments walked backwards.  Bytes per launch: (1 + 4) * B*C*L * sizeof(T) — the
+// algorithmic minimum for a materialised (B,4,C,L) tensor.  (The fused path, ss2d_scan_*.cu with
+// ss2d_cross_*_params, never materialises it.)
+#include "ss2d_common.cuh"
+#include "../../include/ss2d_b200.h"
+
+namespace ss2d {
+
+constexpr int kTile = 32;
+constexpr int kRows = 8;  // blockDim = (32, 8); each thread handles 4 rows of the tile
+
+// x:(BC,H,W) -> xs:(B,4,C,L)
+template <typename T>
+__global__ void __launch_bounds__(kTile *kRows) cross_scan_kernel(const T *__restrict__ x, T *__restrict__ xs, int C,
+                                                                   int H, int W) {
+    __shared__ T tile[kTile][kTile + 1];
+    const int64_t L = (int64_t)H * W;
+    const int tiles_w = (W + kTile - 1) / kTile, tiles_h = (H + kTile - 1) / kTile;
+    const int bc = blockIdx.x / (tiles_w * tiles_h), tile_id = blockIdx.x % (tiles_w * tiles_h);
+    const int b = bc / C, c = bc % C;
+    const int h0 = (tile_id / tiles_w) * kTile, w0 = (tile_id % tiles_w) * kTile;
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const T *src = x + (int64_t)bc * L;
+    T *d0 = xs + (((int64_t)b * 4 + 0) * C + c) * L;
+    T *d1 = d0 + (int64_t)C * L, *d2 = d1 + (int64_t)C * L, *d3 = d2 + (int64_t)C * L;
+#pragma unroll
+    for (int r = 0; r < kTile; r += kRows) {
+        const int h = h0 + ty + r, w = w0 + tx;
+        if (h < H && w < W) {
+            const T v = src[(int64_t)h * W + w];
+            tile[ty + r][tx] = v;
+            const int64_t l = (int64_t)h * W + w;
+            d0[l] = v;
+            d2[L - 1 - l] = v;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < kTile; r += kRows) {
+        const int w = w0 + ty + r, h = h0 + tx;  // consecutive threads walk h: contiguous in the column-major image
+        if (h < H && w < W) {
+            const T v = tile[tx][ty + r];
+            const int64_t l = (int64_t)w * H + h;
+            d1[l] = v;
+            d3[L - 1 - l] = v;
+        }
+    }
+}
+
+// ys:(B,4,C,L) -> y:(B,C,L) spatial;  y = ((ys0 + ys1) + ys2) + ys3 un-permuted, fp32 accumulation (the order of
+// triton_cross_merge, csm_triton.py:72-73).
+template <typename T>
+__global__ void __launch_bounds__(kTile *kRows) cross_merge_kernel(const T *__restrict__ ys, T *__restrict__ y, int C,
+                                                                    int H, int W) {
+    __shared__ float tile[kTile][kTile + 1];
+    const int64_t L = (int64_t)H * W;
+    const int tiles_w = (W + kTile - 1) / kTile, tiles_h = (H + kTile - 1) / kTile;
+    const int bc = blockIdx.x / (tiles_w * tiles_h), tile_id = blockIdx.x % (tiles_w * tiles_h);
+    const int b = bc / C, c = bc % C;
+    const int h0 = (tile_id / tiles_w) * kTile, w0 = (tile_id % tiles_w) * kTile;
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const T *s0 = ys + (((int64_t)b * 4 + 0) * C + c) * L;
+    const T *s1 = s0 + (int64_t)C * L, *s2 = s1 + (int64_t)C * L, *s3 = s2 + (int64_t)C * L;
+#pragma unroll
+    for (int r = 0; r < kTile; r += kRows) {
+        const int w = w0 + ty + r, h = h0 + tx;
+        if (h < H && w < W) {
+            const int64_t l = (int64_t)w * H + h;
+            tile[tx][ty + r] = to_f32<T>(s1[l]);                 // direction 1 at pixel (h, w)
+        }
+    }
+    __syncthreads();
+    float acc[kTile / kRows];
+#pragma unroll
+    for (int r = 0; r < kTile; r += kRows) {
+        const int h = h0 + ty + r, w = w0 + tx;
+        if (h < H && w < W) {
+            const int64_t l = (int64_t)h * W + w;
+            acc[r / kRows] = (to_f32<T>(s0[l]) + tile[ty + r][tx]) + to_f32<T>(s2[L - 1 - l]);
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < kTile; r += kRows) {
+        const int w = w0 + ty + r, h = h0 + tx;
+        if (h < H && w < W) tile[tx][ty + r] = to_f32<T>(s3[L - 1 - ((int64_t)w * H + h)]);  // direction 3
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < kTile; r += kRows) {
+        const int h = h0 + ty + r, w = w0 + tx;
+        if (h < H && w < W) y[(int64_t)bc * L + (int64_t)h * W + w] = from_f32<T>(acc[r / kRows] + tile[ty + r][tx]);
+    }
+}
+
+template <typename T>
+static int launch_cross(bool merge, const void *in, void *out, int64_t B, int64_t C, int64_t H, int64_t W, cudaStream_t s) {
+    dim3 block(kTile, kRows);
+    dim3 grid((unsigned)(((W + kTile - 1) / kTile) * ((H + kTile - 1) / kTile) * B * C));
+    if (merge)
+        cross_merge_kernel<T><<<grid, block, 0, s>>>(static_cast<const T *>(in), static_cast<T *>(out), (int)C, (int)H, (int)W);
+    else
+        cross_scan_kernel<T><<<grid, block, 0, s>>>(static_cast<const T *>(in), static_cast<T *>(out), (int)C, (int)H, (int)W);
+    return (int)cudaGetLastError();
+}
+
+static int cross_dispatch(bool merge, const void *in, void *out, int64_t B, int64_t C, int64_t H, int64_t W, int32_t dtype,
+                          void *stream) {
+    if (!in || !out || B <= 0 || C <= 0 || H <= 0 || W <= 0) return SS2D_EINVAL;
+    if (((W + kTile - 1) / kTile) * ((H + kTile - 1) / kTile) * B * C > 0x7fffffffLL) return SS2D_EINVAL;
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    switch (dtype) {
+        case SS2D_F32: return launch_cross<float>(merge, in, out, B, C, H, W, s);
+        case SS2D_F16: return launch_cross<__half>(merge, in, out, B, C, H, W, s);
+        case SS2D_BF16: return launch_cross<__nv_bfloat16>(merge, in, out, B, C, H, W, s);
+        default: return SS2D_EDTYPE;
+    }
+}
+
+}  // namespace ss2d
+
+extern "C" int ss2d_cross_scan(const void *x, void *xs, int64_t B, int64_t C, int64_t H, int64_t W, int32_t dtype, void *stream) {
+    return ss2d::cross_dispatch(false, x, xs, B, C, H, W, dtype, stream);
+}
+extern "C" int ss2d_cross_merge(const void *ys, void *y, int64_t B, int64_t C, int64_t H, int64_t W, int32_t dtype, void *stream) {
+    return ss2d::cross_dispatch(true, ys, y, B, C, H, W, dtype, stream);
+}

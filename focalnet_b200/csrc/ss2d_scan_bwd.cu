@@ -26,17 +26,16 @@
 
 namespace ss2d {
 
-__device__ __forceinline__ void red_add_v4(float *addr, float a, float b, float c, float d) {
-    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
-}
-
 struct BwdFlags {
     bool vec_u, vec_delta, vec_bc, vec_dout, vec_z, vec_out, vec_dbc, vec_grad;
 };
 
-template <typename in_t, typename out_t, int T, int NW, int SB, int MINB>
+// CROSS (fused seam S3): u and dout are gathered from the spatial-order planes x[b,d] / dy[b,d] with the
+// direction's addressing, and du is accumulated (red.global.add) into the spatial-order fp32 plane dx[b,d]
+// — CrossMerge.backward and CrossScan.backward as load / store addressing.  ddelta, dB, dC stay in scan order.
+template <typename in_t, typename out_t, int T, int NW, int SB, int MINB, bool CROSS>
 __global__ void __launch_bounds__(NW * kWarp, MINB)
-scan_bwd_kernel(const ss2d_scan_bwd_params pb, const int tiles_per_group, const BwdFlags fl) {
+scan_bwd_kernel(const ss2d_scan_bwd_params pb, const int tiles_per_group, const BwdFlags fl, const CrossInfo xinfo) {
     using FT = BCTile<in_t, T, SB>;
     using RL = typename FT::RL;
     using RLf = RowLayout<float, T>;  // staging rows for the dB/dC reduction are fp32
@@ -68,15 +67,17 @@ scan_bwd_kernel(const ss2d_scan_bwd_params pb, const int tiles_per_group, const 
     float *sDx = sHin + NW * Npad;                                           // dx carry from the chunk to the right
     float *sdA = sDx + NW * Npad;                                            // [NW][N][32] per-lane dA partials
 
-    const in_t *u_row = reinterpret_cast<const in_t *>(p.u) + b * p.u_bstride + c * p.u_dstride;
+    const int64_t cu = CROSS ? (active ? c_local : per_g - 1) : c;  // row of u / dout / du: d in fused mode
+    const in_t *u_row = reinterpret_cast<const in_t *>(p.u) + b * p.u_bstride + cu * p.u_dstride;
     const in_t *d_row = reinterpret_cast<const in_t *>(p.delta) + b * p.delta_bstride + c * p.delta_dstride;
     const in_t *z_row = p.z ? reinterpret_cast<const in_t *>(p.z) + b * p.z_bstride + c * p.z_dstride : nullptr;
     const out_t *pre_row = p.z ? reinterpret_cast<const out_t *>(p.out) + b * p.out_bstride + c * p.out_dstride : nullptr;
-    const out_t *g_row = reinterpret_cast<const out_t *>(pb.dout) + b * pb.dout_bstride + c * pb.dout_dstride;
+    const out_t *g_row = reinterpret_cast<const out_t *>(pb.dout) + b * pb.dout_bstride + cu * pb.dout_dstride;
     const in_t *Bg = reinterpret_cast<const in_t *>(p.B) + b * p.B_bstride + g * p.B_gstride;
     const in_t *Cg = reinterpret_cast<const in_t *>(p.C) + b * p.C_bstride + g * p.C_gstride;
     const int64_t row = ((int64_t)b * p.dim + c) * L;
     in_t *du_row = reinterpret_cast<in_t *>(pb.du) + row;
+    float *dx_plane = CROSS ? reinterpret_cast<float *>(pb.du) + ((int64_t)b * per_g + cu) * L : nullptr;
     in_t *dd_row = reinterpret_cast<in_t *>(pb.ddelta) + row;
     in_t *dz_row = pb.dz ? reinterpret_cast<in_t *>(pb.dz) + row : nullptr;
     float *dBg = pb.dB + ((int64_t)b * p.ngroups + g) * N * L;
@@ -118,9 +119,14 @@ scan_bwd_kernel(const ss2d_scan_bwd_params pb, const int tiles_per_group, const 
         const int64_t tl = t0 + lane * T;
         const int valid = (int)min((int64_t)T, L - tl);
         if (sb == 0) {
-            load_block<in_t, T>(u_row + tl, uv, valid, fl.vec_u);
+            if constexpr (CROSS) {
+                load_block_cross<in_t, T>(u_row, uv, g, tl, L, xinfo, fl.vec_u);
+                load_block_cross<out_t, T>(g_row, go, g, tl, L, xinfo, fl.vec_dout);
+            } else {
+                load_block<in_t, T>(u_row + tl, uv, valid, fl.vec_u);
+                load_block<out_t, T>(g_row + tl, go, valid, fl.vec_dout);
+            }
             load_block<in_t, T>(d_row + tl, dl, valid, fl.vec_delta);
-            load_block<out_t, T>(g_row + tl, go, valid, fl.vec_dout);
             if (z_row) {  // out = pre * silu(z): dz and the gated upstream gradient
                 float zv[T], pre[T];
                 load_block<in_t, T>(z_row + tl, zv, valid, fl.vec_z);
@@ -253,7 +259,8 @@ scan_bwd_kernel(const ss2d_scan_bwd_params pb, const int tiles_per_group, const 
                 s[i] = fmaf(dl[i], s[i], Dv * go[i]);  // du
             }
             if (active) {
-                store_block<in_t, T>(du_row + tl, s, valid, fl.vec_grad);
+                if constexpr (CROSS) red_block_cross<T>(dx_plane, s, g, tl, L, xinfo, fl.vec_dbc);
+                else store_block<in_t, T>(du_row + tl, s, valid, fl.vec_grad);
                 store_block<in_t, T>(dd_row + tl, ddl, valid, fl.vec_grad);
             }
             dl_first_right = __shfl_sync(0xffffffffu, dl[0], 0);
@@ -282,8 +289,8 @@ scan_bwd_kernel(const ss2d_scan_bwd_params pb, const int tiles_per_group, const 
 
 static inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
-template <typename in_t, typename out_t, int T, int NW, int MINB>
-static int launch_bwd(const ss2d_scan_bwd_params &pb, cudaStream_t stream) {
+template <typename in_t, typename out_t, int T, int NW, int MINB, bool CROSS = false>
+static int launch_bwd(const ss2d_scan_bwd_params &pb, cudaStream_t stream, CrossInfo xinfo = CrossInfo{0, 0}) {
     constexpr int SB = 8;
     using FT = BCTile<in_t, T, SB>;
     const ss2d_scan_fwd_params &p = pb.f;
@@ -305,11 +312,12 @@ static int launch_bwd(const ss2d_scan_bwd_params &pb, cudaStream_t stream) {
     fl.vec_dbc = aligned16(pb.dB) && aligned16(pb.dC) && p.seqlen % 4 == 0;
     // du / ddelta / dz rows are contiguous (batch, dim, L)
     fl.vec_grad = aligned16(pb.du) && aligned16(pb.ddelta) && (!pb.dz || aligned16(pb.dz)) && (p.seqlen * ei) % 16 == 0;
-    auto kern = scan_bwd_kernel<in_t, out_t, T, NW, SB, MINB>;
+    if (CROSS) fl.vec_dbc = fl.vec_dbc && aligned16(pb.du);  // dx plane rows are L floats: 16-byte aligned iff L % 4 == 0
+    auto kern = scan_bwd_kernel<in_t, out_t, T, NW, SB, MINB, CROSS>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     const int64_t grid = p.batch * p.ngroups * tiles;
-    kern<<<(unsigned)grid, NW * kWarp, smem, stream>>>(pb, tiles, fl);
+    kern<<<(unsigned)grid, NW * kWarp, smem, stream>>>(pb, tiles, fl, xinfo);
     return (int)cudaGetLastError();
 }
 
@@ -348,6 +356,42 @@ extern "C" int ss2d_selective_scan_bwd(const ss2d_scan_bwd_params *pp, void *str
         case SS2D_BF16:
             return p.out_dtype == SS2D_F32 ? launch_bwd<__nv_bfloat16, float, T, NW, MINB>(pb, s)
                                            : launch_bwd<__nv_bfloat16, __nv_bfloat16, T, NW, MINB>(pb, s);
+        default: return SS2D_EDTYPE;
+    }
+}
+
+// Fused SS2D core backward (seam S3): see ss2d_cross_bwd_params in include/ss2d_b200.h.
+extern "C" int ss2d_cross_scan_bwd(const ss2d_cross_bwd_params *pp, void *stream) {
+    if (!pp) return SS2D_EINVAL;
+    const ss2d_cross_fwd_params &c = pp->f;
+    if (!c.x || !c.delta || !c.B || !c.C || !c.A || !pp->dy || !pp->dx || !pp->ddelta || !pp->dA || !pp->dB || !pp->dC)
+        return SS2D_EINVAL;
+    if (c.batch <= 0 || c.D <= 0 || c.H <= 0 || c.W <= 0 || c.dstate <= 0 || c.dstate > SS2D_MAX_DSTATE) return SS2D_EINVAL;
+    if ((c.Dskip && !pp->dDskip) || (c.delta_bias && !pp->ddelta_bias)) return SS2D_EINVAL;
+    const int64_t L = c.H * c.W;
+    ss2d_scan_bwd_params pb{};
+    ss2d_scan_fwd_params &p = pb.f;
+    p.batch = c.batch; p.dim = 4 * c.D; p.seqlen = L; p.dstate = c.dstate; p.ngroups = 4;
+    p.in_dtype = c.in_dtype; p.out_dtype = SS2D_F32; p.delta_softplus = c.delta_softplus;
+    p.u = c.x; p.delta = c.delta; p.A = c.A; p.B = c.B; p.C = c.C; p.D = c.Dskip; p.delta_bias = c.delta_bias;
+    p.u_bstride = c.D * L; p.u_dstride = L;
+    p.delta_bstride = 4 * c.D * L; p.delta_dstride = L;
+    p.B_bstride = p.C_bstride = c.bc_bstride ? c.bc_bstride : 4 * c.dstate * L;
+    p.B_gstride = p.C_gstride = c.bc_gstride ? c.bc_gstride : c.dstate * L;
+    p.B_nstride = p.C_nstride = L;
+    p.ckpt = c.ckpt;
+    pb.dout = pp->dy; pb.dout_bstride = c.D * L; pb.dout_dstride = L;
+    pb.du = pp->dx; pb.ddelta = pp->ddelta;
+    pb.dA = pp->dA; pb.dB = pp->dB; pb.dC = pp->dC; pb.dD = pp->dDskip; pb.ddelta_bias = pp->ddelta_bias;
+    using namespace ss2d;
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    const CrossInfo xi{(int)c.H, (int)c.W};
+    if (!p.ckpt && L > SS2D_CKPT_STEPS) return SS2D_EINVAL;  // the fused backward needs the forward's checkpoints
+    constexpr int T = SS2D_BWD_T, NW = SS2D_BWD_NW, MINB = SS2D_BWD_MINB;
+    switch (c.in_dtype) {
+        case SS2D_F32: return launch_bwd<float, float, T, NW, MINB, true>(pb, s, xi);
+        case SS2D_F16: return launch_bwd<__half, float, T, NW, MINB, true>(pb, s, xi);
+        case SS2D_BF16: return launch_bwd<__nv_bfloat16, float, T, NW, MINB, true>(pb, s, xi);
         default: return SS2D_EDTYPE;
     }
 }

@@ -187,9 +187,12 @@ __device__ __forceinline__ void fwd_block_pipelined(const unsigned char *buf, in
     }
 }
 
-template <typename in_t, typename out_t, int T, int NW, int SB, int BATCH, int MINB>
+// CROSS: fused seam S3.  The groups are the 4 scan directions, `u` is the spatial-order plane x[b, d] shared by
+// the 4 directions (u_dstride indexes d, not k*D+d) and `out` is the merged spatial-order fp32 plane y[b, d],
+// accumulated with red.global.add (zero-filled by the caller).  delta / B / C stay in scan order.
+template <typename in_t, typename out_t, int T, int NW, int SB, int BATCH, int MINB, bool CROSS>
 __global__ void __launch_bounds__(NW * kWarp, MINB)
-scan_fwd_kernel(const ss2d_scan_fwd_params p, const int tiles_per_group, const FwdFlags fl) {
+scan_fwd_kernel(const ss2d_scan_fwd_params p, const int tiles_per_group, const FwdFlags fl, const CrossInfo xinfo) {
     using FT = BCTile<in_t, T, SB>;
     using RL = typename FT::RL;
     constexpr int chunk = FT::chunk;
@@ -215,12 +218,13 @@ scan_fwd_kernel(const ss2d_scan_fwd_params p, const int tiles_per_group, const F
     float *sP = reinterpret_cast<float *>(smem + 2 * FT::tile_bytes) + NW * Npad + warp * Npad;  // running prod a (for x)
     float *sCk = reinterpret_cast<float *>(smem + 2 * FT::tile_bytes) + 2 * NW * Npad + warp * SLOTS * Npad;  // [SLOTS][Npad]
 
-    const in_t *u_row = reinterpret_cast<const in_t *>(p.u) + b * p.u_bstride + c * p.u_dstride;
+    const int64_t cu = CROSS ? (active ? c_local : per_g - 1) : c;  // row of u / out: d in fused mode
+    const in_t *u_row = reinterpret_cast<const in_t *>(p.u) + b * p.u_bstride + cu * p.u_dstride;
     const in_t *d_row = reinterpret_cast<const in_t *>(p.delta) + b * p.delta_bstride + c * p.delta_dstride;
     const in_t *z_row = p.z ? reinterpret_cast<const in_t *>(p.z) + b * p.z_bstride + c * p.z_dstride : nullptr;
     const in_t *Bg = reinterpret_cast<const in_t *>(p.B) + b * p.B_bstride + g * p.B_gstride;
     const in_t *Cg = reinterpret_cast<const in_t *>(p.C) + b * p.C_bstride + g * p.C_gstride;
-    out_t *o_row = p.out ? reinterpret_cast<out_t *>(p.out) + b * p.out_bstride + c * p.out_dstride : nullptr;
+    out_t *o_row = p.out ? reinterpret_cast<out_t *>(p.out) + b * p.out_bstride + cu * p.out_dstride : nullptr;
     out_t *oz_row = p.out_z ? reinterpret_cast<out_t *>(p.out_z) + b * p.out_bstride + c * p.out_dstride : nullptr;
     const float Dv = p.D ? p.D[c] : 0.f;
     const float bias = p.delta_bias ? p.delta_bias[c] : 0.f;
@@ -260,11 +264,12 @@ scan_fwd_kernel(const ss2d_scan_fwd_params p, const int tiles_per_group, const F
 #pragma unroll
             for (int i = 0; i < T; ++i) { uv[i] = 0.01f * (lane + i); dl[i] = 0.02f * (lane - i) + ci; }
 #else
-            load_block<in_t, T>(u_row + tl, uv, valid, fl.vec_u);
+            if constexpr (CROSS) load_block_cross<in_t, T>(u_row, uv, g, tl, L, xinfo, fl.vec_u);
+            else load_block<in_t, T>(u_row + tl, uv, valid, fl.vec_u);
             load_block<in_t, T>(d_row + tl, dl, valid, fl.vec_delta);
 #endif
             if (tl + chunk < L) {  // pull the next chunk's u / delta lines into L2 while this chunk computes
-                prefetch_l2(u_row + tl + chunk);
+                if constexpr (!CROSS) prefetch_l2(u_row + tl + chunk);
                 prefetch_l2(d_row + tl + chunk);
             }
 #pragma unroll
@@ -304,7 +309,9 @@ scan_fwd_kernel(const ss2d_scan_fwd_params p, const int tiles_per_group, const F
         if (sb == n_sb - 1) {  // chunk finished
             __syncwarp();
             if (active) {
-                if (o_row) {
+                if constexpr (CROSS) {
+                    red_block_cross<T>(reinterpret_cast<float *>(o_row), y, g, tl, L, xinfo, fl.vec_out);
+                } else if (o_row) {
 #if SS2D_KNOCK == 7
                     if (y[0] == 123.4f)
 #endif
@@ -341,8 +348,8 @@ scan_fwd_kernel(const ss2d_scan_fwd_params p, const int tiles_per_group, const F
 
 static inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
-template <typename in_t, typename out_t, int T = 16, int NW = 8, int BATCH = 1, int MINB = 2, int SB = 8>
-static int launch_fwd(const ss2d_scan_fwd_params &p, cudaStream_t stream) {
+template <typename in_t, typename out_t, int T = 16, int NW = 8, int BATCH = 1, int MINB = 2, int SB = 8, bool CROSS = false>
+static int launch_fwd(const ss2d_scan_fwd_params &p, cudaStream_t stream, CrossInfo ci = CrossInfo{0, 0}) {
     using FT = BCTile<in_t, T, SB>;
     const int per_g = (int)(p.dim / p.ngroups);
     const int tiles = (per_g + NW - 1) / NW;
@@ -359,11 +366,11 @@ static int launch_fwd(const ss2d_scan_fwd_params &p, cudaStream_t stream) {
                  (p.out_dstride * eo) % 16 == 0;
     fl.vec_z = p.z && aligned16(p.z) && (p.z_bstride * ei) % 16 == 0 && (p.z_dstride * ei) % 16 == 0;
     static_assert(BATCH == 0 || SB % BATCH == 0, "BATCH must divide the state block (0 = software-pipelined)");
-    auto kern = scan_fwd_kernel<in_t, out_t, T, NW, SB, BATCH, MINB>;
+    auto kern = scan_fwd_kernel<in_t, out_t, T, NW, SB, BATCH, MINB, CROSS>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     const int64_t grid = p.batch * p.ngroups * tiles;
-    kern<<<(unsigned)grid, NW * kWarp, smem, stream>>>(p, tiles, fl);
+    kern<<<(unsigned)grid, NW * kWarp, smem, stream>>>(p, tiles, fl, ci);
     return (int)cudaGetLastError();
 }
 
@@ -416,6 +423,36 @@ extern "C" int ss2d_selective_scan_fwd(const ss2d_scan_fwd_params *pp, void *str
         case SS2D_BF16:
             return p.out_dtype == SS2D_F32 ? launch_fwd<__nv_bfloat16, float>(p, s)
                                            : launch_fwd<__nv_bfloat16, __nv_bfloat16>(p, s);
+        default: return SS2D_EDTYPE;
+    }
+}
+
+// Fused SS2D core forward (seam S3): see ss2d_cross_fwd_params in include/ss2d_b200.h.
+extern "C" int ss2d_cross_scan_fwd(const ss2d_cross_fwd_params *pp, void *stream) {
+    if (!pp) return SS2D_EINVAL;
+    const ss2d_cross_fwd_params &c = *pp;
+    if (!c.x || !c.delta || !c.B || !c.C || !c.A || !c.y) return SS2D_EINVAL;
+    if (c.batch <= 0 || c.D <= 0 || c.H <= 0 || c.W <= 0 || c.dstate <= 0 || c.dstate > SS2D_MAX_DSTATE) return SS2D_EINVAL;
+    if (c.H * c.W > 0x7fffffffLL || c.batch * 4 * c.D > 0x7fffffffLL) return SS2D_EINVAL;
+    const int64_t L = c.H * c.W;
+    ss2d_scan_fwd_params p{};
+    p.batch = c.batch; p.dim = 4 * c.D; p.seqlen = L; p.dstate = c.dstate; p.ngroups = 4;
+    p.in_dtype = c.in_dtype; p.out_dtype = SS2D_F32; p.delta_softplus = c.delta_softplus;
+    p.u = c.x; p.delta = c.delta; p.A = c.A; p.B = c.B; p.C = c.C; p.D = c.Dskip; p.delta_bias = c.delta_bias;
+    p.u_bstride = c.D * L; p.u_dstride = L;
+    p.delta_bstride = 4 * c.D * L; p.delta_dstride = L;
+    p.B_bstride = p.C_bstride = c.bc_bstride ? c.bc_bstride : 4 * c.dstate * L;
+    p.B_gstride = p.C_gstride = c.bc_gstride ? c.bc_gstride : c.dstate * L;
+    p.B_nstride = p.C_nstride = L;
+    p.out = c.y; p.out_bstride = c.D * L; p.out_dstride = L;
+    p.ckpt = c.ckpt;
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    using namespace ss2d;
+    const CrossInfo ci{(int)c.H, (int)c.W};
+    switch (c.in_dtype) {
+        case SS2D_F32: return launch_fwd<float, float, 16, 8, 1, 2, 8, true>(p, s, ci);
+        case SS2D_F16: return launch_fwd<__half, float, 16, 8, 1, 2, 8, true>(p, s, ci);
+        case SS2D_BF16: return launch_fwd<__nv_bfloat16, float, 16, 8, 1, 2, 8, true>(p, s, ci);
         default: return SS2D_EDTYPE;
     }
 }

@@ -149,7 +149,7 @@ def scan_bwd(u, delta, A, B, C, D, delta_bias, dout, x=None, delta_softplus=Fals
     _chk(dout.is_cuda and (dout.dtype == u.dtype or dout.dtype == torch.float32), "selective_scan: bad dout dtype")
     _chk(tuple(dout.shape) == (batch, dim, L), "selective_scan: dout must have shape (batch, dim, seqlen)")
     _chk(dout.stride(-1) == 1 or L == 1, "selective_scan: dout.stride(-1) must be 1")
-    if _n_ref(L) > 1:
+    if _n_ref(L) > 1 and ckpt is None:
         _chk(x is not None, "selective_scan: x is required when seqlen > 2048")  # oflex.cpp:315
     if x is not None:
         _chk(x.dtype == torch.float32 and x.is_cuda and tuple(x.shape) == (batch, dim, _n_ref(L), 2 * N),

@@ -1,0 +1,326 @@
+"""Host-side mirror of the SS2D core seams S2 and S3 (ITS/models/vmamba_layers.py, ITS/models/csm_triton.py).
+
+* ``CrossScan`` / ``CrossMerge`` (aliases ``CrossScanTriton`` / ``CrossMergeTriton``): autograd Functions with the
+  reference's signatures (csm_triton.py:163-210; torch twins vmamba_layers.py:29-71) on the CUDA kernels of
+  ``csrc/ss2d_cross.cu`` — no Triton.
+* ``cross_selective_scan``: same signature and result as the reference function (vmamba_layers.py:200-299) but
+  the 4-direction CrossScan / CrossMerge are folded into the scan kernels' addressing
+  (``ss2d_cross_scan_fwd/_bwd``): the (B,4,D,L) copies of x and of the scan outputs are never materialised.
+* ``dwconv_silu``: the permute + depthwise 3x3 conv + SiLU pre-mix of SS2D.forwardv2 (vmamba_layers.py:591-594).
+* ``patch_ss2d``: re-binds ``forward_core`` of every SS2D in an *unchanged* reference model to the fused path.
+
+torch is plumbing (allocation, the two skinny projection GEMMs through cuBLAS, LayerNorm); no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from functools import partial
+
+import torch
+import torch.nn.functional as F
+
+from . import _lib
+from .selective_scan import _DT, C_byref, _chk, _n_fine, _ptr, _stream, build_selective_scan_fn, scan_bwd, scan_fwd
+
+
+# --------------------------------------------------------------------------------------------- S2
+def _cross(op: str, src: torch.Tensor, dst: torch.Tensor, B, Cn, H, W):
+    _chk(src.is_cuda and src.dtype in _DT, "cross scan/merge: CUDA float32/float16/bfloat16 tensors only (no CPU path)")
+    fn = getattr(_lib.lib(), op)
+    with torch.cuda.device(src.device):
+        _lib.check(fn(src.data_ptr(), dst.data_ptr(), B, Cn, H, W, _DT[src.dtype], _stream(src)), op)
+    return dst
+
+
+def cross_scan(x: torch.Tensor) -> torch.Tensor:
+    """(B,C,H,W) -> (B,4,C,H*W)"""
+    B, Cn, H, W = x.shape
+    x = x.contiguous()
+    return _cross("ss2d_cross_scan", x, x.new_empty((B, 4, Cn, H * W)), B, Cn, H, W)
+
+
+def cross_merge(ys: torch.Tensor, H: int, W: int) -> torch.Tensor:
+    """(B,4,C,H*W) -> (B,C,H*W)"""
+    B, K, Cn = ys.shape[:3]
+    _chk(K == 4, "cross_merge expects 4 directions")
+    ys = ys.contiguous()
+    return _cross("ss2d_cross_merge", ys, ys.new_empty((B, Cn, H * W)), B, Cn, H, W)
+
+
+class CrossScan(torch.autograd.Function):
+    """CrossScanTriton (csm_triton.py:163-185): forward (B,C,H,W)->(B,4,C,L); backward is a cross-merge."""
+
+    @staticmethod
+    def forward(ctx, x: torch.Tensor):
+        ctx.shape = x.shape
+        return cross_scan(x)
+
+    @staticmethod
+    def backward(ctx, ys: torch.Tensor):
+        B, Cn, H, W = ctx.shape
+        return cross_merge(ys, H, W).view(B, Cn, H, W)
+
+
+class CrossMerge(torch.autograd.Function):
+    """CrossMergeTriton (csm_triton.py:188-210): forward (B,4,C,H,W)->(B,C,L); backward is a cross-scan."""
+
+    @staticmethod
+    def forward(ctx, ys: torch.Tensor):
+        B, K, Cn, H, W = ys.shape
+        ctx.shape = (B, Cn, H, W)
+        return cross_merge(ys.reshape(B, K, Cn, H * W), H, W)
+
+    @staticmethod
+    def backward(ctx, dy: torch.Tensor):
+        B, Cn, H, W = ctx.shape
+        return cross_scan(dy.reshape(B, Cn, H, W)).view(B, 4, Cn, H, W)
+
+
+CrossScanTriton, CrossMergeTriton = CrossScan, CrossMerge
+
+
+# ------------------------------------------------------------------------------------- selective scan seams
+class _SelectiveScanBase(torch.autograd.Function):
+    """SelectiveScanOflex / SelectiveScanCore (vmamba_layers.py:155-196) on the C ABI."""
+    OFLEX = True
+
+    @classmethod
+    def _fwd(cls, ctx, u, delta, A, B, Cm, D=None, delta_bias=None, delta_softplus=False, nrows=1, backnrows=1, oflex=True):
+        ctx.delta_softplus = delta_softplus
+        out, x, ckpt, _ = scan_fwd(u, delta, A, B, Cm, D, delta_bias, delta_softplus, 1, out_float=(oflex and cls.OFLEX))
+        ctx.save_for_backward(u, delta, A, B, Cm, D, delta_bias, ckpt)
+        return out
+
+    @staticmethod
+    def _bwd(ctx, dout):
+        u, delta, A, B, Cm, D, delta_bias, ckpt = ctx.saved_tensors
+        if dout.stride(-1) != 1:
+            dout = dout.contiguous()
+        du, ddelta, dA, dB, dC, dD, dbias, _ = scan_bwd(u, delta, A, B, Cm, D, delta_bias, dout, None, ctx.delta_softplus, 1,
+                                                        ckpt=ckpt)
+        return du, ddelta, dA, dB, dC, dD, dbias, None, None, None, None
+
+
+class SelectiveScanOflex(_SelectiveScanBase):
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda")
+    def forward(ctx, u, delta, A, B, C, D=None, delta_bias=None, delta_softplus=False, nrows=1, backnrows=1, oflex=True):
+        return SelectiveScanOflex._fwd(ctx, u, delta, A, B, C, D, delta_bias, delta_softplus, nrows, backnrows, oflex)
+
+    @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
+    def backward(ctx, dout, *args):
+        return _SelectiveScanBase._bwd(ctx, dout)
+
+
+class SelectiveScanCore(_SelectiveScanBase):
+    OFLEX = False
+
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda")
+    def forward(ctx, u, delta, A, B, C, D=None, delta_bias=None, delta_softplus=False, nrows=1, backnrows=1, oflex=True):
+        return SelectiveScanCore._fwd(ctx, u, delta, A, B, C, D, delta_bias, delta_softplus, nrows, backnrows, oflex)
+
+    @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
+    def backward(ctx, dout, *args):
+        return _SelectiveScanBase._bwd(ctx, dout)
+
+
+# --------------------------------------------------------------------------------------------- S3
+class FusedCrossScanFn(torch.autograd.Function):
+    """x (B,D,H,W) spatial, delta (B,4D,L) / Bs, Cs (B,4,N,L) in scan order  ->  y (B,D,L) spatial fp32 =
+    CrossMerge(selective_scan(CrossScan(x), ...)) without the 4x copies (ss2d_cross_scan_fwd/_bwd)."""
+
+    @staticmethod
+    def forward(ctx, x, delta, A, Bs, Cs, Ds, delta_bias, delta_softplus=True):
+        B, D, H, W = x.shape
+        L, N = H * W, A.shape[1]
+        _chk(x.is_cuda and x.dtype in _DT, "fused SS2D core: x must be a CUDA float32/float16/bfloat16 tensor")
+        _chk(delta.dtype == x.dtype and Bs.dtype == x.dtype and Cs.dtype == x.dtype, "fused SS2D core: dtype mismatch")
+        _chk(tuple(delta.shape) == (B, 4 * D, L) and tuple(A.shape) == (4 * D, N), "fused SS2D core: bad delta / A shape")
+        _chk(tuple(Bs.shape) == (B, 4, N, L) and tuple(Cs.shape) == (B, 4, N, L), "fused SS2D core: bad B / C shape")
+        x, delta, A = x.contiguous(), delta.contiguous(), A.contiguous().float()
+        if not (Bs.stride(3) == 1 and Bs.stride(2) == L and Bs.stride() == Cs.stride()):
+            Bs, Cs = Bs.contiguous(), Cs.contiguous()
+        Ds = None if Ds is None else Ds.contiguous().float()
+        delta_bias = None if delta_bias is None else delta_bias.contiguous().float()
+        y = torch.zeros((B, D, L), device=x.device, dtype=torch.float32)
+        ckpt = torch.empty((B, 4 * D, _n_fine(L), N), device=x.device, dtype=torch.float32)
+        P = _lib.CrossFwdParams()
+        FusedCrossScanFn._fill(P, x, delta, A, Bs, Cs, Ds, delta_bias, delta_softplus, (B, D, H, W, N))
+        P.y, P.ckpt = y.data_ptr(), ckpt.data_ptr()
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.lib().ss2d_cross_scan_fwd(C_byref(P), _stream(x)), "ss2d_cross_scan_fwd")
+        ctx.save_for_backward(x, delta, A, Bs, Cs, Ds, delta_bias, ckpt)
+        ctx.delta_softplus = delta_softplus
+        return y
+
+    @staticmethod
+    def _fill(P, x, delta, A, Bs, Cs, Ds, delta_bias, delta_softplus, dims):
+        B, D, H, W, N = dims
+        P.batch, P.D, P.H, P.W, P.dstate = B, D, H, W, N
+        P.in_dtype, P.delta_softplus = _DT[x.dtype], int(bool(delta_softplus))
+        P.x, P.delta, P.B, P.C, P.A = x.data_ptr(), delta.data_ptr(), Bs.data_ptr(), Cs.data_ptr(), A.data_ptr()
+        P.Dskip, P.delta_bias = _ptr(Ds), _ptr(delta_bias)
+        P.bc_bstride, P.bc_gstride = Bs.stride(0), Bs.stride(1)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, delta, A, Bs, Cs, Ds, delta_bias, ckpt = ctx.saved_tensors
+        B, D, H, W = x.shape
+        L, N = H * W, A.shape[1]
+        dy = dy.contiguous().float()
+        dx = torch.zeros((B, D, L), device=x.device, dtype=torch.float32)
+        ddelta = torch.empty_like(delta)
+        dA = torch.zeros_like(A)
+        dB = torch.zeros((B, 4, N, L), device=x.device, dtype=torch.float32)
+        dC = torch.zeros_like(dB)
+        dDs = torch.zeros_like(Ds) if Ds is not None else None
+        dbias = torch.zeros_like(delta_bias) if delta_bias is not None else None
+        P = _lib.CrossBwdParams()
+        FusedCrossScanFn._fill(P.f, x, delta, A, Bs, Cs, Ds, delta_bias, ctx.delta_softplus, (B, D, H, W, N))
+        P.f.ckpt = ckpt.data_ptr()
+        P.dy, P.dx, P.ddelta = dy.data_ptr(), dx.data_ptr(), ddelta.data_ptr()
+        P.dA, P.dB, P.dC, P.dDskip, P.ddelta_bias = dA.data_ptr(), dB.data_ptr(), dC.data_ptr(), _ptr(dDs), _ptr(dbias)
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.lib().ss2d_cross_scan_bwd(C_byref(P), _stream(x)), "ss2d_cross_scan_bwd")
+        return dx.view(B, D, H, W).to(x.dtype), ddelta, dA, dB.to(Bs.dtype), dC.to(Cs.dtype), dDs, dbias, None
+
+
+def _to_scan_order(t: torch.Tensor, H: int, W: int) -> torch.Tensor:
+    """t (B,4,C,L) holding direction k's rows in SPATIAL order -> each direction's own scan order.  Only ever
+    applied to the small x_dbl (R+2N = 38 rows per direction), never to x (d_inner = 192 rows)."""
+    B, K, Cn, L = t.shape
+    out = torch.empty_like(t)
+    out[:, 0] = t[:, 0]
+    out[:, 1] = t[:, 1].view(B, Cn, H, W).transpose(2, 3).reshape(B, Cn, L)
+    out[:, 2] = t[:, 2].flip(-1)
+    out[:, 3] = t[:, 3].view(B, Cn, H, W).transpose(2, 3).reshape(B, Cn, L).flip(-1)
+    return out
+
+
+def cross_selective_scan(
+    x: torch.Tensor = None,
+    x_proj_weight: torch.Tensor = None,
+    x_proj_bias: torch.Tensor = None,
+    dt_projs_weight: torch.Tensor = None,
+    dt_projs_bias: torch.Tensor = None,
+    A_logs: torch.Tensor = None,
+    Ds: torch.Tensor = None,
+    delta_softplus=True,
+    out_norm: torch.nn.Module = None,
+    out_norm_shape="v0",
+    to_dtype=True,
+    force_fp32=False,
+    nrows=-1,
+    backnrows=-1,
+    ssoflex=True,
+    SelectiveScan=None,
+    CrossScan=None,
+    CrossMerge=None,
+    no_einsum=False,
+    dt_low_rank=True,
+):
+    """Drop-in for the reference ``cross_selective_scan`` (vmamba_layers.py:200-299): same arguments, same
+    (B,H,W,D) result.  ``SelectiveScan`` / ``CrossScan`` / ``CrossMerge`` / ``nrows`` / ``no_einsum`` select
+    implementations in the reference; here they are accepted and ignored — there is one implementation.
+
+    x_proj is pointwise over pixels, so x_dbl_k = W_k x is computed ONCE from x in spatial order and only that
+    38-row tensor is permuted into each direction's scan order; x itself (192 rows) is read by the scan kernel
+    with the direction's addressing."""
+    B, D, H, W = x.shape
+    N = A_logs.shape[1]
+    K, _, R = dt_projs_weight.shape
+    L = H * W
+    _chk(K == 4 and dt_low_rank, "fused SS2D core supports the 4-direction low-rank-dt configuration of the model")
+    xin = x.float() if force_fp32 else x
+    xf = xin.reshape(B, D, L)
+    x_dbl = torch.matmul(x_proj_weight.reshape(K * (R + 2 * N), D).to(xf.dtype), xf)  # (B, K*(R+2N), L) spatial
+    if x_proj_bias is not None:
+        x_dbl = x_dbl + x_proj_bias.reshape(1, -1, 1).to(x_dbl.dtype)
+    x_dbl = _to_scan_order(x_dbl.view(B, K, R + 2 * N, L), H, W)
+    dts_lr, Bs, Cs = torch.split(x_dbl, [R, N, N], dim=2)
+    dts = torch.matmul(dt_projs_weight.to(x_dbl.dtype).unsqueeze(0), dts_lr).reshape(B, K * D, L)  # scan order
+    As = -torch.exp(A_logs.to(torch.float))
+    y = FusedCrossScanFn.apply(xin, dts, As, Bs, Cs, Ds.to(torch.float), dt_projs_bias.reshape(-1).to(torch.float),
+                               delta_softplus)
+    if out_norm_shape in ["v1"]:
+        y = out_norm(y.view(B, -1, H, W)).permute(0, 2, 3, 1)
+    else:
+        y = out_norm(y.transpose(1, 2).contiguous()).view(B, H, W, -1)
+    return y.to(x.dtype) if to_dtype else y
+
+
+def patch_ss2d(model: torch.nn.Module) -> int:
+    """Re-bind ``forward_core`` (an instance attribute, vmamba_layers.py:451) of every SS2D module of an unchanged
+    reference model to the fused path via the ``cross_selective_scan=`` hook of forward_corev2 (:566).  Returns the
+    number of modules patched."""
+    n = 0
+    for m in model.modules():
+        if hasattr(m, "forward_corev2") and hasattr(m, "forward_core"):
+            m.forward_core = partial(m.forward_corev2, cross_selective_scan=cross_selective_scan)
+            n += 1
+    return n
+
+
+# ------------------------------------------------------------------------------------- dwconv + SiLU pre-mix
+class DwConvSiLUFn(torch.autograd.Function):
+    """xz (B,H,W,Cs) channels-last (first C channels convolved), weight (C,1,3,3), bias (C)|None
+    -> silu(dwconv3x3(x) + bias) as (B,C,H,W)."""
+
+    @staticmethod
+    def forward(ctx, xz, weight, bias, Cn):
+        _chk(xz.is_cuda and xz.dtype == torch.float32, "dwconv_silu: float32 CUDA tensors only (no CPU path)")
+        B, H, W, Cs = xz.shape
+        _chk(xz.stride(3) == 1 and xz.is_contiguous(), "dwconv_silu: xz must be contiguous channels-last")
+        w = weight.reshape(Cn, 9).contiguous().float()
+        bb = None if bias is None else bias.contiguous().float()
+        out = torch.empty((B, Cn, H, W), device=xz.device, dtype=torch.float32)
+        with torch.cuda.device(xz.device):
+            _lib.check(_lib.lib().ss2d_dwconv_silu_fwd(xz.data_ptr(), Cs, w.data_ptr(), _ptr(bb), out.data_ptr(), B, Cn, H, W,
+                                                      _stream(xz)), "ss2d_dwconv_silu_fwd")
+        ctx.save_for_backward(xz, w, bb)
+        ctx.Cn, ctx.wshape, ctx.has_bias = Cn, weight.shape, bias is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        xz, w, bb = ctx.saved_tensors
+        B, H, W, Cs = xz.shape
+        Cn = ctx.Cn
+        dout = dout.contiguous().float()
+        dxz = torch.zeros_like(xz)
+        dw = torch.zeros_like(w)
+        db = torch.zeros(Cn, device=xz.device, dtype=torch.float32) if ctx.has_bias else None
+        scratch = torch.empty((B, H, W, Cn), device=xz.device, dtype=torch.float32)
+        with torch.cuda.device(xz.device):
+            _lib.check(_lib.lib().ss2d_dwconv_silu_bwd(xz.data_ptr(), Cs, w.data_ptr(), _ptr(bb), dout.data_ptr(),
+                                                      scratch.data_ptr(), dxz.data_ptr(), Cs, dw.data_ptr(), _ptr(db), B, Cn, H,
+                                                      W, _stream(xz)), "ss2d_dwconv_silu_bwd")
+        return dxz, dw.view(ctx.wshape), db, None
+
+
+def dwconv_silu(xz, weight, bias=None, channels=None):
+    return DwConvSiLUFn.apply(xz, weight, bias, channels or weight.shape[0])
+
+
+def smoke_fused():
+    """One tiny fused forward+backward on cuda:0 checked against the CPU oracle (called by __graft_entry__.smoke)."""
+    import numpy as np
+    from oracle import ss2d_oracle as orc
+    g = torch.Generator().manual_seed(3)
+    B, D, H, W, N = 1, 8, 6, 10, 16
+    L = H * W
+    x = torch.randn(B, D, H, W, generator=g).cuda()
+    delta = (0.5 * torch.rand(B, 4 * D, L, generator=g)).cuda()
+    A = (-0.5 * torch.rand(4 * D, N, generator=g)).cuda()
+    Bs, Cs = torch.randn(B, 4, N, L, generator=g).cuda(), torch.randn(B, 4, N, L, generator=g).cuda()
+    Ds, bias = torch.randn(4 * D, generator=g).cuda(), (0.5 * torch.rand(4 * D, generator=g)).cuda()
+    y = FusedCrossScanFn.apply(x, delta, A, Bs, Cs, Ds, bias, True)
+    xs = orc.cross_scan(x).reshape(B, 4 * D, L)
+    f = orc.scan_fwd(xs, delta, A, Bs, Cs, Ds, None, bias, True)
+    ref = orc.cross_merge(f["out"].reshape(B, 4, D, H, W))
+    err = float(np.abs(y.cpu().numpy() - ref).max() / np.abs(ref).max())
+    print(f"[smoke] fused SS2D core vs CPU oracle: max rel err {err:.2e}")
+    assert err < 1e-3, err

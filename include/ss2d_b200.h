@@ -110,15 +110,17 @@ int ss2d_cross_scan(const void *x, void *xs, int64_t B, int64_t C, int64_t H, in
 int ss2d_cross_merge(const void *ys, void *y, int64_t B, int64_t C, int64_t H, int64_t W, int32_t dtype, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
- * fused SS2D core (seam S3): operands in SPATIAL order, the four scan directions are applied in the
- * kernel's load / store addressing — no (B,4,D,L) copy of x or of y is ever materialised.
- *   x      : (batch, D, H, W)            in_dtype, contiguous           (u of all four directions)
- *   delta  : (batch, 4, D, H*W)          in_dtype, spatial order l=h*W+w (dt_proj output, pre-softplus)
- *   B, C   : (batch, 4, dstate, H*W)     in_dtype, spatial order
+ * fused SS2D core (seam S3): CrossScan and CrossMerge are applied in the scan kernel's load / store
+ * addressing — no (B,4,D,L) copy of x (100.7 MB at the microbench) and no (B,4,D,L) ys is ever materialised.
+ *   x      : (batch, D, H, W)         in_dtype, contiguous, SPATIAL order: the u of all four directions; the
+ *            kernel of direction k reads pixel perm_k(l) for scan step l (vmamba_layers.py:35-37)
+ *   delta  : (batch, 4*D, H*W)        in_dtype, SCAN order of each direction (dt_proj output, pre-softplus)
+ *   B, C   : (batch, 4, dstate, H*W)  in_dtype, SCAN order of each direction.  delta/B/C are projections of the
+ *            38-row x_dbl, which the host permutes per direction before dt_proj — 5x fewer bytes than permuting x
  *   A (4*D,dstate), Dskip (4*D), delta_bias (4*D) : f32, channel index k*D+d (vmamba_layers.py:273-279)
- *   y      : (batch, D, H*W) f32, spatial order, = CrossMerge of the four scans; MUST BE ZEROED (directions
- *            are accumulated with red.global.add.f32)
- *   ckpt   : (batch, 4*D, ceil(L/256), dstate) f32 or NULL
+ *   y      : (batch, D, H*W) f32, SPATIAL order, = CrossMerge of the four scans; MUST BE ZEROED by the caller
+ *            (each direction accumulates with red.global.add.f32, so the sum order is not deterministic)
+ *   ckpt   : (batch, 4*D, ceil(L/256), dstate) f32 — h every 256 scan steps, consumed by the backward
  * ------------------------------------------------------------------------------------------- */
 typedef struct ss2d_cross_fwd_params {
     int64_t batch, D, H, W, dstate;
@@ -127,10 +129,15 @@ typedef struct ss2d_cross_fwd_params {
     const float *A, *Dskip, *delta_bias;
     float *y;
     float *ckpt;
+    int64_t bc_bstride, bc_gstride; /* element strides of B and C over batch / direction (rows of dstate are L apart);
+                                       0 = contiguous.  Lets B, C be views into the permuted x_dbl (no .contiguous() copy) */
 } ss2d_cross_fwd_params;
 
-/*   dy : (batch, D, H*W) f32 spatial.  dx (batch,D,H*W) f32 ZEROED; ddelta (batch,4,D,H*W) in_dtype;
- *   dB, dC (batch,4,dstate,H*W) f32 ZEROED; dA (4*D,dstate), dDskip, ddelta_bias (4*D) f32 ZEROED.      */
+/*   dy : (batch, D, H*W) f32 spatial (gathered per direction = CrossMerge.backward).
+ *   dx : (batch, D, H*W) f32 spatial, ZEROED (du of the 4 directions accumulated = CrossScan.backward);
+ *   ddelta (batch,4*D,L) in_dtype scan order; dB, dC (batch,4,dstate,L) f32 scan order ZEROED;
+ *   dA (4*D,dstate), dDskip, ddelta_bias (4*D) f32 ZEROED.  f.ckpt (from the forward) is required when L > 256;
+ *   ckpt_scratch is reserved (must be NULL).                                                              */
 typedef struct ss2d_cross_bwd_params {
     ss2d_cross_fwd_params f;
     const float *dy;
@@ -148,13 +155,14 @@ int ss2d_cross_scan_bwd(const ss2d_cross_bwd_params *p, void *stream);
  *   xin  : (batch, H, W, cstride) f32 — first C channels of every pixel are convolved (the in_proj
  *          output keeps x | z interleaved per pixel, vmamba_layers.py:585-587)
  *   weight (C,3,3), bias (C) or NULL : f32 ;  out : (batch, C, H, W) f32
- * bwd: dout (batch,C,H,W) -> dxin (batch,H,W,dx_cstride) first C channels written; dweight (C,9), dbias (C) ZEROED
+ * bwd: dout (batch,C,H,W) -> dxin (batch,H,W,dx_cstride) first C channels written; dweight (C,9), dbias (C)
+ *      f32 ZEROED (accumulated); dpre_scratch (batch,H,W,C) f32 work buffer
  * ------------------------------------------------------------------------------------------- */
 int ss2d_dwconv_silu_fwd(const float *xin, int64_t cstride, const float *weight, const float *bias, float *out,
                          int64_t batch, int64_t C, int64_t H, int64_t W, void *stream);
 int ss2d_dwconv_silu_bwd(const float *xin, int64_t cstride, const float *weight, const float *bias, const float *dout,
-                         float *dxin, int64_t dx_cstride, float *dweight, float *dbias, int64_t batch, int64_t C,
-                         int64_t H, int64_t W, void *stream);
+                         float *dpre_scratch, float *dxin, int64_t dx_cstride, float *dweight, float *dbias,
+                         int64_t batch, int64_t C, int64_t H, int64_t W, void *stream);
 
 #ifdef __cplusplus
 }

@@ -50,6 +50,6 @@ def make_scan_inputs(batch, dim, N, L, G, dtype=torch.float32, device="cuda", se
 def rel_err(a, b, floor=1e-3):
     """max |a-b| / max(max |b|, floor) — the 'relative' of the north star's 1e-3 / 1e-2 gates.  The floor keeps
     an identically-zero reference (e.g. dA when L == 1) from turning fp32 rounding noise into an infinite ratio."""
-    a = torch.as_tensor(a).double().cpu()
-    b = torch.as_tensor(b).double().cpu()
+    a = torch.as_tensor(a).detach().double().cpu()
+    b = torch.as_tensor(b).detach().double().cpu()
     return float((a - b).abs().max() / b.abs().max().clamp_min(floor))

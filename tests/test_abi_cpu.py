@@ -36,7 +36,7 @@ def test_struct_layout_matches_header(lib):
     from focalnet_b200 import _lib
     assert ctypes.sizeof(_lib.ScanFwdParams) == 5 * 8 + 4 * 4 + 8 * 8 + 12 * 8 + 8 + 16 + 8 * 3
     assert ctypes.sizeof(_lib.ScanBwdParams) == ctypes.sizeof(_lib.ScanFwdParams) + 8 + 16 + 8 + 8 * 8
-    assert ctypes.sizeof(_lib.CrossFwdParams) == 5 * 8 + 2 * 4 + 9 * 8
+    assert ctypes.sizeof(_lib.CrossFwdParams) == 5 * 8 + 2 * 4 + 9 * 8 + 2 * 8
     assert ctypes.sizeof(_lib.CrossBwdParams) == ctypes.sizeof(_lib.CrossFwdParams) + 9 * 8
 
 

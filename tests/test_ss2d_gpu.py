@@ -1,0 +1,158 @@
+"""GPU parity of CrossScan/CrossMerge (S2), the fused SS2D core (S3), the dwconv+SiLU pre-mix and the drop-in
+modules.  Checkers: golden vectors produced by the Python reference (tests/golden), the C oracle, and — for the
+fused core at model shapes — the unfused composition of this library's own S1/S2 kernels."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from tests._util import rel_err
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _t(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def test_cross_scan_merge_match_reference_golden():
+    from focalnet_b200 import cross_merge, cross_scan
+    g = dict(np.load(os.path.join(GOLDEN, "cross.npz")))
+    for tag in "abc":
+        x, ys = _t(g[f"{tag}_x"]), _t(g[f"{tag}_ys"])
+        B, K, C, H, W = ys.shape
+        assert torch.equal(cross_scan(x).cpu(), torch.from_numpy(g[f"{tag}_xs"]))       # pure data movement: bit-exact
+        assert rel_err(cross_merge(ys.view(B, K, C, H * W), H, W), g[f"{tag}_y"]) < 1e-6
+
+
+@pytest.mark.parametrize("shape", [(2, 5, 64, 64), (1, 3, 30, 40), (1, 2, 33, 7), (2, 4, 1, 50)])
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+def test_cross_scan_merge_vs_oracle_and_autograd(shape, dt):
+    from focalnet_b200 import CrossMerge, CrossScan
+    from oracle import ss2d_oracle as orc
+    B, C, H, W = shape
+    g = torch.Generator().manual_seed(H * W)
+    x = torch.randn(*shape, generator=g).to(dt).cuda().requires_grad_()
+    ys = torch.randn(B, 4, C, H, W, generator=g).to(dt).cuda().requires_grad_()
+    xs = CrossScan.apply(x)
+    assert torch.equal(xs.float().cpu(), torch.from_numpy(orc.cross_scan(x.detach().float())))
+    y = CrossMerge.apply(ys)
+    tol = 1e-6 if dt == torch.float32 else 1e-2
+    assert rel_err(y, orc.cross_merge(ys.detach().float())) < tol
+    # backward of one is the forward of the other (csm_triton.py:177-185,202-210)
+    gy = torch.randn(B, 4, C, H * W, generator=g).to(dt).cuda()
+    xs.backward(gy)
+    assert rel_err(x.grad, orc.cross_merge(gy.float().view(B, 4, C, H, W)).reshape(B, C, H, W)) < tol
+    gm = torch.randn(B, C, H * W, generator=g).to(dt).cuda()
+    y.backward(gm)
+    assert torch.equal(ys.grad.float().cpu().reshape(B, 4, C, H * W), torch.from_numpy(orc.cross_scan(gm.float().view(B, C, H, W))))
+
+
+@pytest.mark.parametrize("name", ["small", "n16"])
+def test_fused_core_matches_reference_golden(name):
+    """cross_selective_scan (vmamba_layers.py:200-299) executed by the Python reference on CPU vs our fused path."""
+    from focalnet_b200 import cross_selective_scan
+    g = {k: _t(v) for k, v in np.load(os.path.join(GOLDEN, f"fused_{name}.npz")).items()}
+    D = g["x"].shape[1]
+    ln = torch.nn.LayerNorm(D).cuda()
+    with torch.no_grad():
+        ln.weight.copy_(g["ln_weight"]); ln.bias.copy_(g["ln_bias"])
+    leaves = {k: g[k].clone().requires_grad_() for k in ("x", "x_proj_weight", "dt_projs_weight", "dt_projs_bias", "A_logs", "Ds")}
+    y = cross_selective_scan(leaves["x"], leaves["x_proj_weight"], None, leaves["dt_projs_weight"], leaves["dt_projs_bias"],
+                             leaves["A_logs"], leaves["Ds"], delta_softplus=True, out_norm=ln, out_norm_shape="v0")
+    assert rel_err(y, g["y_noeinsum1"]) < 1e-3 and rel_err(y, g["y_noeinsum0"]) < 1e-3
+    y.backward(g["dy"])
+    for k, gk in (("x", "dx"), ("x_proj_weight", "dx_proj_weight"), ("dt_projs_weight", "ddt_projs_weight"),
+                  ("dt_projs_bias", "ddt_projs_bias"), ("A_logs", "dA_logs"), ("Ds", "dDs")):
+        assert rel_err(leaves[k].grad, g[gk]) < 1e-3, k
+    assert rel_err(ln.weight.grad, g["dln_weight"]) < 1e-3 and rel_err(ln.bias.grad, g["dln_bias"]) < 1e-3
+
+
+@pytest.mark.parametrize("shape", [(2, 192, 64, 64), (1, 192, 30, 40), (1, 24, 17, 23), (1, 8, 128, 128)])
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+def test_fused_core_equals_unfused_composition(shape, dt):
+    """Fused kernels (directions in the addressing) == CrossScan -> selective scan -> CrossMerge, fwd and bwd."""
+    from focalnet_b200 import CrossMerge, CrossScan, FusedCrossScanFn, SelectiveScanOflex
+    B, D, H, W = shape
+    N, L = 16, H * W
+    g = torch.Generator().manual_seed(L + D)
+    mk = lambda *s: torch.randn(*s, generator=g)
+    x = mk(B, D, H, W).to(dt).cuda()
+    delta = (0.5 * torch.rand(B, 4 * D, L, generator=g)).to(dt).cuda()
+    A = (-0.5 * torch.rand(4 * D, N, generator=g)).cuda()
+    Bs, Cs = mk(B, 4, N, L).to(dt).cuda(), mk(B, 4, N, L).to(dt).cuda()
+    Ds, bias = mk(4 * D).cuda(), (0.5 * torch.rand(4 * D, generator=g)).cuda()
+    dy = mk(B, D, L).cuda()
+    a = [t.clone().requires_grad_() for t in (x, delta, A, Bs, Cs, Ds, bias)]
+    b = [t.clone().requires_grad_() for t in (x, delta, A, Bs, Cs, Ds, bias)]
+    y1 = FusedCrossScanFn.apply(*a, True)
+    xs = CrossScan.apply(b[0]).view(B, 4 * D, L)
+    ys = SelectiveScanOflex.apply(xs, b[1], b[2], b[3], b[4], b[5], b[6], True, 1, 1, True)
+    y2 = CrossMerge.apply(ys.view(B, 4, D, H, W))
+    tol = 1e-4 if dt == torch.float32 else 1e-2
+    assert rel_err(y1, y2) < tol
+    y1.backward(dy); y2.backward(dy)
+    for ta, tb, name in zip(a, b, ("dx", "ddelta", "dA", "dB", "dC", "dD", "dbias")):
+        assert rel_err(ta.grad, tb.grad) < tol, name
+
+
+def test_dwconv_silu_matches_reference_golden():
+    from focalnet_b200 import dwconv_silu
+    g = {k: _t(v) for k, v in np.load(os.path.join(GOLDEN, "dwconv.npz")).items()}
+    C = g["weight"].shape[0]
+    xz, w, b = (g[k].clone().requires_grad_() for k in ("xz", "weight", "bias"))
+    y = dwconv_silu(xz, w, b, C)
+    assert rel_err(y, g["y"]) < 1e-5
+    y.backward(g["dy"])
+    assert rel_err(xz.grad, g["dxz"]) < 1e-5 and rel_err(w.grad, g["dweight"]) < 1e-5 and rel_err(b.grad, g["dbias"]) < 1e-5
+
+
+@pytest.mark.parametrize("shape", [(2, 64, 64, 192), (1, 30, 40, 192), (1, 7, 5, 20)])
+def test_dwconv_silu_vs_torch_library(shape):
+    """Against the library ops the reference calls (permute + nn.Conv2d depthwise + SiLU), in fp64."""
+    from focalnet_b200 import dwconv_silu
+    B, H, W, C = shape
+    g = torch.Generator().manual_seed(C + H)
+    xz = torch.randn(B, H, W, 2 * C, generator=g).cuda().requires_grad_()
+    w = (0.3 * torch.randn(C, 1, 3, 3, generator=g)).cuda().requires_grad_()
+    b = (0.1 * torch.randn(C, generator=g)).cuda().requires_grad_()
+    dy = torch.randn(B, C, H, W, generator=g).cuda()
+    y = dwconv_silu(xz, w, b, C)
+    y.backward(dy)
+    xr, wr, br = (t.detach().double().requires_grad_() for t in (xz, w, b))
+    yr = torch.nn.functional.silu(torch.nn.functional.conv2d(xr[..., :C].permute(0, 3, 1, 2), wr, br, padding=1, groups=C))
+    yr.backward(dy.double())
+    assert rel_err(y, yr) < 1e-5
+    assert rel_err(xz.grad, xr.grad) < 1e-5 and rel_err(w.grad, wr.grad) < 1e-4 and rel_err(b.grad, br.grad) < 1e-4
+
+
+def test_dropin_modules_have_reference_signatures():
+    """`import selective_scan_cuda_oflex` / `_core` / `csm_triton` resolve to this library and behave like the
+    reference modules (selective_scan_oflex.cpp:360-363; vmamba_layers.py:183,193)."""
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(__file__)), "focalnet_b200", "dropin"))
+    try:
+        for m in ("selective_scan_cuda_oflex", "selective_scan_cuda_core", "csm_triton"):
+            sys.modules.pop(m, None)
+        import csm_triton
+        import selective_scan_cuda_core
+        import selective_scan_cuda_oflex
+        from oracle import ss2d_oracle as orc
+        from tests._util import make_scan_inputs
+        d = make_scan_inputs(1, 8, 16, 2300, 2, dtype=torch.bfloat16, seed=4)
+        args = (d["u"], d["delta"], d["A"], d["B"], d["C"], d["D"], d["delta_bias"])
+        out, x = selective_scan_cuda_oflex.fwd(*args, True, 1, True)
+        assert out.dtype == torch.float32 and tuple(x.shape) == (1, 8, 2, 32)
+        res = selective_scan_cuda_oflex.bwd(*args, d["dout"], x, True, 1)
+        assert len(res) == 7 and res[0].dtype == torch.bfloat16 and res[3].dtype == torch.bfloat16 and res[2].dtype == torch.float32
+        out_c, _ = selective_scan_cuda_core.fwd(*args, True, 1)
+        assert out_c.dtype == torch.bfloat16
+        f = orc.scan_fwd(*args[:5], d["D"], None, d["delta_bias"], True)
+        b = orc.scan_bwd(*args[:5], d["D"], None, d["delta_bias"], d["dout"], True)
+        assert rel_err(out, f["out"]) < 1e-2 and rel_err(res[0], b["du"]) < 3e-2 and rel_err(res[2], b["dA"]) < 3e-2
+        xs = csm_triton.CrossScanTriton.apply(torch.randn(1, 2, 4, 6).cuda())
+        assert tuple(xs.shape) == (1, 4, 2, 24)
+    finally:
+        sys.path.pop(0)
