@@ -17,6 +17,8 @@
 #include "ss2d_common.cuh"
 #include "ss2d_scan_tile.cuh"
 #include "../../include/ss2d_b200.h"
+#include <cstdlib>
+#include <cstring>
 
 #ifndef SS2D_BWD_T
 #define SS2D_BWD_T 8
@@ -33,7 +35,7 @@ struct BwdFlags {
 // CROSS (fused seam S3): u and dout are gathered from the spatial-order planes x[b,d] / dy[b,d] with the
 // direction's addressing, and du is accumulated (red.global.add) into the spatial-order fp32 plane dx[b,d]
 // — CrossMerge.backward and CrossScan.backward as load / store addressing.  ddelta, dB, dC stay in scan order.
-template <typename in_t, typename out_t, int T, int NW, int SB, int MINB, bool CROSS>
+template <typename in_t, typename out_t, int T, int NW, int SB, int MINB, bool CROSS, bool DIRECT_RED>
 __global__ void __launch_bounds__(NW * kWarp, MINB)
 scan_bwd_kernel(const ss2d_scan_bwd_params pb, const int tiles_per_group, const BwdFlags fl, const CrossInfo xinfo) {
     using FT = BCTile<in_t, T, SB>;
@@ -172,24 +174,28 @@ scan_bwd_kernel(const ss2d_scan_bwd_params pb, const int tiles_per_group, const 
             float a[T], hv[T], Bv[T], Cv[T];
             lds_block<in_t, T>(buf + r * RL::row_bytes, lane, Bv);
 #pragma unroll
-            for (int i = 0; i < T; ++i) a[i] = ex2(dl[i] * A2);
-            // ---- prefix recurrence: pass 1, warp scan, pass 2 (materialise h) ----
-            float H = du[0] * Bv[0];
+            float bb[T];
 #pragma unroll
-            for (int i = 1; i < T; ++i) H = fmaf(a[i], H, du[i] * Bv[i]);
+            for (int i = 0; i < T; ++i) { a[i] = ex2(dl[i] * A2); bb[i] = du[i] * Bv[i]; }
+            // ---- prefix recurrence: pass 1, warp scan, pass 2 (materialise h) ----
+            float H = bb[0];
+#pragma unroll
+            for (int i = 1; i < T; ++i) H = fmaf(a[i], H, bb[i]);
             float P = ex2(A2 * dsum);
             warp_scan_inclusive(P, H, lane);
             float Pe = __shfl_up_sync(0xffffffffu, P, 1), He = __shfl_up_sync(0xffffffffu, H, 1);
             if (lane == 0) { Pe = 1.f; He = 0.f; }
             float h = fmaf(Pe, sHin[warp * Npad + n], He);
 #pragma unroll
-            for (int i = 0; i < T; ++i) { h = fmaf(a[i], h, du[i] * Bv[i]); hv[i] = h; }
+            for (int i = 0; i < T; ++i) { h = fmaf(a[i], h, bb[i]); hv[i] = h; }
             // ---- suffix recurrence on (a_{t+1}, dout_t C_t) ----
             lds_block<in_t, T>(buf + (SB + r) * RL::row_bytes, lane, Cv);
-            const float a_last = ex2(A2 * dlnext);  // a at the step following this lane's block
-            float R = go[T - 1] * Cv[T - 1];
 #pragma unroll
-            for (int i = T - 2; i >= 0; --i) R = fmaf(a[i + 1], R, go[i] * Cv[i]);
+            for (int i = 0; i < T; ++i) Cv[i] *= go[i];  // g_t = dout_t C_t
+            const float a_last = ex2(A2 * dlnext);  // a at the step following this lane's block
+            float R = Cv[T - 1];
+#pragma unroll
+            for (int i = T - 2; i >= 0; --i) R = fmaf(a[i + 1], R, Cv[i]);
             float Qp = ex2(A2 * qsum);
             warp_rscan_inclusive(Qp, R, lane);
             float Qe = __shfl_down_sync(0xffffffffu, Qp, 1), Re = __shfl_down_sync(0xffffffffu, R, 1);
@@ -202,17 +208,33 @@ scan_bwd_kernel(const ss2d_scan_bwd_params pb, const int tiles_per_group, const 
 #pragma unroll
             for (int i = T - 1; i >= 0; --i) {
                 const float an = i == T - 1 ? a_last : a[i + 1];
-                dx = fmaf(an, dx, go[i] * Cv[i]);
+                dx = fmaf(an, dx, Cv[i]);
                 dCv[i] = go[i] * hv[i];
                 dBv[i] = dx * du[i];
                 s[i] = fmaf(dx, Bv[i], s[i]);
-                const float ah = fmaf(-du[i], Bv[i], hv[i]);  // a_t h_{t-1}
-                const float pq = dx * ah;
+                const float pq = dx * (hv[i] - bb[i]);  // dx_t * a_t h_{t-1}
                 w[i] = fmaf(An, pq, w[i]);
                 dA_acc = fmaf(dl[i], pq, dA_acc);
             }
             if (lane == 0) sDx[warp * Npad + n] = dx;  // dx at this chunk's first step -> carry for the left chunk
             sdA[(warp * N + n) * kWarp + lane] += dA_acc;
+            if constexpr (DIRECT_RED) {
+                // ---- dB/dC: every warp adds its channel's contribution straight into L2 (red.global.add.v4) ----
+                if (active) {
+                    float *dB_dst = dBg + (int64_t)n * L + tl, *dC_dst = dCg + (int64_t)n * L + tl;
+                    if (fl.vec_dbc && valid >= T) {
+#pragma unroll
+                        for (int i = 0; i < T; i += 4) {
+                            red_add_v4(dB_dst + i, dBv[i], dBv[i + 1], dBv[i + 2], dBv[i + 3]);
+                            red_add_v4(dC_dst + i, dCv[i], dCv[i + 1], dCv[i + 2], dCv[i + 3]);
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < T; ++i)
+                            if (i < valid) { red_add_f32(dB_dst + i, dBv[i]); red_add_f32(dC_dst + i, dCv[i]); }
+                    }
+                }
+            } else {
             // ---- dB/dC: reduce over the CTA's channels, then one vector reduction per 4 steps ----
             if (!active) {
 #pragma unroll
@@ -246,6 +268,7 @@ scan_bwd_kernel(const ss2d_scan_bwd_params pb, const int tiles_per_group, const 
                 }
             }
             __syncthreads();
+            }
         }
         if (sb == n_sb - 1) {  // chunk finished: du, ddelta
             float ddl[T];
@@ -289,7 +312,7 @@ scan_bwd_kernel(const ss2d_scan_bwd_params pb, const int tiles_per_group, const 
 
 static inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
-template <typename in_t, typename out_t, int T, int NW, int MINB, bool CROSS = false>
+template <typename in_t, typename out_t, int T, int NW, int MINB, bool CROSS = false, bool DIRECT_RED = false>
 static int launch_bwd(const ss2d_scan_bwd_params &pb, cudaStream_t stream, CrossInfo xinfo = CrossInfo{0, 0}) {
     constexpr int SB = 8;
     using FT = BCTile<in_t, T, SB>;
@@ -313,7 +336,7 @@ static int launch_bwd(const ss2d_scan_bwd_params &pb, cudaStream_t stream, Cross
     // du / ddelta / dz rows are contiguous (batch, dim, L)
     fl.vec_grad = aligned16(pb.du) && aligned16(pb.ddelta) && (!pb.dz || aligned16(pb.dz)) && (p.seqlen * ei) % 16 == 0;
     if (CROSS) fl.vec_dbc = fl.vec_dbc && aligned16(pb.du);  // dx plane rows are L floats: 16-byte aligned iff L % 4 == 0
-    auto kern = scan_bwd_kernel<in_t, out_t, T, NW, SB, MINB, CROSS>;
+    auto kern = scan_bwd_kernel<in_t, out_t, T, NW, SB, MINB, CROSS, DIRECT_RED>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     const int64_t grid = p.batch * p.ngroups * tiles;
@@ -348,6 +371,20 @@ extern "C" int ss2d_selective_scan_bwd(const ss2d_scan_bwd_params *pp, void *str
     }
     using namespace ss2d;
     constexpr int T = SS2D_BWD_T, NW = SS2D_BWD_NW, MINB = SS2D_BWD_MINB;
+#ifdef SS2D_TUNE  // development knob: SS2D_BWD_CFG=TxNWxMINBx{s|d} (s = smem-staged dB/dC reduction, d = direct RED)
+    if (p.in_dtype == SS2D_F32) {
+        const char *cfg = getenv("SS2D_BWD_CFG");
+        if (cfg) {
+            if (!strcmp(cfg, "8x8x2xd")) return launch_bwd<float, float, 8, 8, 2, false, true>(pb, s);
+            if (!strcmp(cfg, "8x8x3xd")) return launch_bwd<float, float, 8, 8, 3, false, true>(pb, s);
+            if (!strcmp(cfg, "8x4x4xd")) return launch_bwd<float, float, 8, 4, 4, false, true>(pb, s);
+            if (!strcmp(cfg, "8x16x1xs")) return launch_bwd<float, float, 8, 16, 1, false, false>(pb, s);
+            if (!strcmp(cfg, "8x16x1xd")) return launch_bwd<float, float, 8, 16, 1, false, true>(pb, s);
+            if (!strcmp(cfg, "16x8x1xs")) return launch_bwd<float, float, 16, 8, 1, false, false>(pb, s);
+            if (!strcmp(cfg, "16x8x1xd")) return launch_bwd<float, float, 16, 8, 1, false, true>(pb, s);
+        }
+    }
+#endif
     switch (p.in_dtype) {
         case SS2D_F32: return launch_bwd<float, float, T, NW, MINB>(pb, s);
         case SS2D_F16:

@@ -33,6 +33,30 @@ __global__ void k_ffma(float *out, float seed) {
     float s = 0; for (int i = 0; i < ILP; ++i) s += v[i];
     if (s == 123.456f) out[0] = s;
 }
+// FFMA with three DISTINCT source registers per instruction (no operand reuse between neighbours)
+__global__ void k_ffma3(float *out, float seed) {
+    float v[ILP], a[ILP], b[ILP];
+#pragma unroll
+    for (int i = 0; i < ILP; ++i) { v[i] = seed + i; a[i] = seed * 0.5f + i * 1e-3f + threadIdx.x * 1e-7f; b[i] = 1.f - 1e-3f * i; }
+    for (int it = 0; it < ITERS; ++it) {
+#pragma unroll
+        for (int i = 0; i < ILP; ++i) v[i] = fmaf(a[i], v[(i + 3) % ILP], b[(i + 5) % ILP]);
+    }
+    float s = 0; for (int i = 0; i < ILP; ++i) s += v[i];
+    if (s == 123.456f) out[0] = s;
+}
+// FMUL with two distinct registers
+__global__ void k_fmul2(float *out, float seed) {
+    float v[ILP], a[ILP];
+#pragma unroll
+    for (int i = 0; i < ILP; ++i) { v[i] = seed + i; a[i] = 1.f - 1e-4f * i - threadIdx.x * 1e-9f; }
+    for (int it = 0; it < ITERS; ++it) {
+#pragma unroll
+        for (int i = 0; i < ILP; ++i) v[i] = v[(i + 3) % ILP] * a[i];
+    }
+    float s = 0; for (int i = 0; i < ILP; ++i) s += v[i];
+    if (s == 123.456f) out[0] = s;
+}
 // R FFMA per MUFU, independent chains
 template <int R> __global__ void k_mix(float *out, float seed) {
     float v[ILP], w[ILP]; float a = seed, b = seed * 0.5f;
@@ -112,6 +136,8 @@ int main() {
     };
     rep("MUFU.EX2", time_ms([&] { k_mufu<<<blocks, threads>>>(out, 0.5f); }), 1);
     rep("FFMA (reg,reg,reg)", time_ms([&] { k_ffma<<<blocks, threads>>>(out, 0.5f); }), 1);
+    rep("FFMA (3 distinct regs)", time_ms([&] { k_ffma3<<<blocks, threads>>>(out, 0.5f); }), 1);
+    rep("FMUL (2 distinct regs)", time_ms([&] { k_fmul2<<<blocks, threads>>>(out, 0.5f); }), 1);
     rep("mix 4 FFMA : 1 MUFU (total)", time_ms([&] { k_mix<4><<<blocks, threads>>>(out, 0.5f); }), 5);
     rep("mix 6 FFMA : 1 MUFU (total)", time_ms([&] { k_mix<6><<<blocks, threads>>>(out, 0.5f); }), 7);
     rep("mix 8 FFMA : 1 MUFU (total)", time_ms([&] { k_mix<8><<<blocks, threads>>>(out, 0.5f); }), 9);
