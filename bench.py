@@ -182,6 +182,7 @@ def main():
 
     import torch.distributed as dist
     from focalnet_b200 import _lib, scan_bwd, scan_fwd
+    from focalnet_b200.sharding import max_over_ranks
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: focalnet_b200 has no CPU path (use --impl reference for the CPU arm)")
     _lib.lib()  # fail loudly if the CUDA library is missing
@@ -220,10 +221,7 @@ def main():
     ms = e0.elapsed_time(e1)
     n_launch = launches[0]
     clocks = sampler.stop()
-    if world > 1:
-        t = torch.tensor([ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+    ms = max_over_ranks(ms, dev)  # the slowest rank defines the job time
 
     s_in = 4 if dtype == torch.float32 else 2
     fb, bb = algorithmic_bytes(WORK["batch"], WORK["dim"], WORK["dstate"], WORK["seqlen"], WORK["ngroups"], s_in, 4)
@@ -292,10 +290,7 @@ def main():
     e1.record()
     barrier()
     e2e_ms = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3) / e2e_steps
-    if world > 1:
-        t = torch.tensor([e2e_ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_ms = float(t.item())
+    e2e_ms = max_over_ranks(e2e_ms, dev)
     e2e = {"value": (fb + bb) * world / (e2e_ms * 1e-3) / 1e9, "unit": "GB/s", "ms_per_step": e2e_ms,
            "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": res_host.numel() * 4}
 

@@ -244,6 +244,35 @@ __device__ __forceinline__ void lds_block(const unsigned char *row, int lane, fl
     for (int i = 0; i < RL::units; ++i) unpack16<T>(src[i], &v[i * RL::per]);
 }
 
+// ---- shared memory by 32-bit address + compile-time immediate ------------------------------------------
+// The scan kernels are bound by instruction issue; addressing every shared operand as
+// [one base register + immediate] keeps integer address arithmetic out of the state loop.
+template <int OFF> __device__ __forceinline__ float lds_f32(uint32_t a) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(v) : "r"(a), "n"(OFF));
+    return v;
+}
+template <int OFF> __device__ __forceinline__ void sts_f32(uint32_t a, float v) {
+    asm volatile("st.shared.f32 [%0+%1], %2;" ::"r"(a), "n"(OFF), "f"(v) : "memory");
+}
+template <int OFF> __device__ __forceinline__ uint4 lds_v4(uint32_t a) {
+    uint4 q;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4+%5];" : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w) : "r"(a), "n"(OFF));
+    return q;
+}
+template <int OFF> __device__ __forceinline__ void sts_v4(uint32_t a, const uint4 &q) {
+    asm volatile("st.shared.v4.u32 [%0+%1], {%2,%3,%4,%5};" ::"r"(a), "n"(OFF), "r"(q.x), "r"(q.y), "r"(q.z), "r"(q.w) : "memory");
+}
+// this lane's TT elements of the padded row that starts OFF bytes after `a` (a already includes the lane offset)
+template <typename T, int TT, int OFF> __device__ __forceinline__ void lds_row(uint32_t a, float (&v)[TT]) {
+    using RL = RowLayout<T, TT>;
+    static_assert(RL::units <= 4, "lane block larger than 64 bytes");
+    if constexpr (RL::units >= 1) unpack16<T>(lds_v4<OFF + 0>(a), &v[0 * RL::per]);
+    if constexpr (RL::units >= 2) unpack16<T>(lds_v4<OFF + 16>(a), &v[1 * RL::per]);
+    if constexpr (RL::units >= 3) unpack16<T>(lds_v4<OFF + 32>(a), &v[2 * RL::per]);
+    if constexpr (RL::units >= 4) unpack16<T>(lds_v4<OFF + 48>(a), &v[3 * RL::per]);
+}
+
 // ---- the scan combine (a0,b0) o (a1,b1) = (a1 a0, a1 b0 + b1)  (selective_scan_common.h:93-95) ----
 // Inclusive Kogge-Stone scan over the 32 lanes of the block aggregates (P = prod a, H = local h_end).
 __device__ __forceinline__ void warp_scan_inclusive(float &P, float &H, int lane) {

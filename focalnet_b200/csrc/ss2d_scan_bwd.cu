@@ -32,10 +32,123 @@ struct BwdFlags {
     bool vec_u, vec_delta, vec_bc, vec_dout, vec_z, vec_out, vec_dbc, vec_grad;
 };
 
+// One state (index R of the staged block) of one chunk for this lane's T steps.
+//   bc   : shared address of this lane's block in row 0 of the staged B tile (C rows SB rows later)
+//   wa   : shared address of this warp's [A*log2e | h entering the chunk | dx carry] arrays (NSB bytes apart)
+//          at the block's first state;  da: this lane's dA partial sums (128 bytes per state)
+//   st   : this lane's slot in the fp32 staging rows of its warp (dB row, then dC row `stage_row` bytes later)
+template <typename in_t, int T, int SB, int R, int NSB_CT, int NW>
+__device__ __forceinline__ void bwd_state(uint32_t bc, uint32_t wa, int nsb_rt, uint32_t da, uint32_t st, uint32_t rd,
+                                          int lane, bool active, bool reducer, float *red_dst, bool red_vec, int red_valid,
+                                          const float (&dl)[T], const float (&du)[T], const float (&go)[T], float (&s)[T],
+                                          float (&w)[T], float dsum, float qsum, float dlnext) {
+    using RL = RowLayout<in_t, T>;
+    using RLf = RowLayout<float, T>;
+    constexpr int stage_row = RLf::row_bytes;
+    const float A2 = lds_f32<R * 4>(wa);
+    const float An = A2 * (1.f / kLog2e);
+    float a[T], hv[T], Bv[T], Cv[T], bb[T];
+    lds_row<in_t, T, R * RL::row_bytes>(bc, Bv);
+#pragma unroll
+    for (int i = 0; i < T; ++i) { a[i] = ex2(dl[i] * A2); bb[i] = du[i] * Bv[i]; }
+    // ---- prefix recurrence: pass 1, warp scan, pass 2 (materialise h) ----
+    float H = bb[0];
+#pragma unroll
+    for (int i = 1; i < T; ++i) H = fmaf(a[i], H, bb[i]);
+    float P = ex2(A2 * dsum);
+    warp_scan_inclusive(P, H, lane);
+    float Pe = __shfl_up_sync(0xffffffffu, P, 1), He = __shfl_up_sync(0xffffffffu, H, 1);
+    if (lane == 0) { Pe = 1.f; He = 0.f; }
+    const uint32_t hin_addr = wa + (NSB_CT > 0 ? NSB_CT : nsb_rt);
+    float h = fmaf(Pe, lds_f32<R * 4>(hin_addr), He);
+#pragma unroll
+    for (int i = 0; i < T; ++i) { h = fmaf(a[i], h, bb[i]); hv[i] = h; }
+    // ---- suffix recurrence on (a_{t+1}, dout_t C_t) ----
+    lds_row<in_t, T, (SB + R) * RL::row_bytes>(bc, Cv);
+#pragma unroll
+    for (int i = 0; i < T; ++i) Cv[i] *= go[i];  // g_t = dout_t C_t
+    const float a_last = ex2(A2 * dlnext);        // a at the step following this lane's block
+    float Rr = Cv[T - 1];
+#pragma unroll
+    for (int i = T - 2; i >= 0; --i) Rr = fmaf(a[i + 1], Rr, Cv[i]);
+    float Qp = ex2(A2 * qsum);
+    warp_rscan_inclusive(Qp, Rr, lane);
+    float Qe = __shfl_down_sync(0xffffffffu, Qp, 1), Re = __shfl_down_sync(0xffffffffu, Rr, 1);
+    if (lane == 31) { Qe = 1.f; Re = 0.f; }
+    const uint32_t dx_addr = wa + (NSB_CT > 0 ? 2 * NSB_CT : 2 * nsb_rt);
+    float dx = fmaf(Qe, lds_f32<R * 4>(dx_addr), Re);  // dx at the first step right of this lane's block
+    // ---- gradients, walking the block right to left ----
+    float dBv[T], dCv[T];
+    float dA_acc = 0.f;
+#pragma unroll
+    for (int i = T - 1; i >= 0; --i) {
+        const float an = i == T - 1 ? a_last : a[i + 1];
+        dx = fmaf(an, dx, Cv[i]);
+        dCv[i] = go[i] * hv[i];
+        dBv[i] = dx * du[i];
+        s[i] = fmaf(dx, Bv[i], s[i]);
+        const float pq = dx * (hv[i] - bb[i]);  // dx_t * a_t h_{t-1}
+        w[i] = fmaf(An, pq, w[i]);
+        dA_acc = fmaf(dl[i], pq, dA_acc);
+    }
+    if (lane == 0) sts_f32<R * 4>(dx_addr, dx);  // dx at this chunk's first step -> carry for the left chunk
+    sts_f32<R * 128>(da, lds_f32<R * 128>(da) + dA_acc);
+    // ---- dB/dC: reduce over the CTA's channels in shared memory, then one vector reduction per 4 steps ----
+    if (!active) {
+#pragma unroll
+        for (int i = 0; i < T; ++i) { dBv[i] = 0.f; dCv[i] = 0.f; }
+    }
+#pragma unroll
+    for (int i = 0; i < T / 4; ++i) {
+        if (i == 0) { sts_v4<0>(st, pack16<float>(&dBv[0])); sts_v4<stage_row>(st, pack16<float>(&dCv[0])); }
+        if (i == 1) { sts_v4<16>(st, pack16<float>(&dBv[4])); sts_v4<stage_row + 16>(st, pack16<float>(&dCv[4])); }
+        if (i == 2) { sts_v4<32>(st, pack16<float>(&dBv[8])); sts_v4<stage_row + 32>(st, pack16<float>(&dCv[8])); }
+        if (i == 3) { sts_v4<48>(st, pack16<float>(&dBv[12])); sts_v4<stage_row + 48>(st, pack16<float>(&dCv[12])); }
+    }
+    __syncthreads();
+    if (reducer) {
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#define SS2D_ACC(WW)                                                                  \
+        if constexpr (WW < NW) {                                                      \
+            const uint4 q = lds_v4<WW * 2 * stage_row>(rd);                           \
+            acc.x += __uint_as_float(q.x); acc.y += __uint_as_float(q.y);            \
+            acc.z += __uint_as_float(q.z); acc.w += __uint_as_float(q.w);            \
+        }
+        SS2D_ACC(0) SS2D_ACC(1) SS2D_ACC(2) SS2D_ACC(3) SS2D_ACC(4) SS2D_ACC(5) SS2D_ACC(6) SS2D_ACC(7)
+        SS2D_ACC(8) SS2D_ACC(9) SS2D_ACC(10) SS2D_ACC(11) SS2D_ACC(12) SS2D_ACC(13) SS2D_ACC(14) SS2D_ACC(15)
+#undef SS2D_ACC
+        static_assert(NW <= 16, "reduction unrolled for at most 16 warps");
+        if (red_vec && red_valid >= 4) {
+            red_add_v4(red_dst, acc.x, acc.y, acc.z, acc.w);
+        } else {
+            if (red_valid > 0) atomicAdd(red_dst + 0, acc.x);
+            if (red_valid > 1) atomicAdd(red_dst + 1, acc.y);
+            if (red_valid > 2) atomicAdd(red_dst + 2, acc.z);
+            if (red_valid > 3) atomicAdd(red_dst + 3, acc.w);
+        }
+    }
+    __syncthreads();
+}
+
+template <typename in_t, int T, int SB, int NSB_CT, int NW, int R = 0>
+__device__ __forceinline__ void bwd_block(uint32_t bc, uint32_t wa, int nsb_rt, uint32_t da, uint32_t st, uint32_t rd, int lane,
+                                          bool active, bool reducer, float *red_dst, int64_t L, bool red_vec, int red_valid,
+                                          const float (&dl)[T], const float (&du)[T], const float (&go)[T], float (&s)[T],
+                                          float (&w)[T], float dsum, float qsum, float dlnext, int n_here) {
+    if constexpr (R < SB) {
+        if (R < n_here) {  // uniform across the CTA: the barriers inside bwd_state are safe
+            bwd_state<in_t, T, SB, R, NSB_CT, NW>(bc, wa, nsb_rt, da, st, rd, lane, active, reducer, red_dst, red_vec,
+                                                 red_valid, dl, du, go, s, w, dsum, qsum, dlnext);
+            bwd_block<in_t, T, SB, NSB_CT, NW, R + 1>(bc, wa, nsb_rt, da, st, rd, lane, active, reducer, red_dst + L, L,
+                                                     red_vec, red_valid, dl, du, go, s, w, dsum, qsum, dlnext, n_here);
+        }
+    }
+}
+
 // CROSS (fused seam S3): u and dout are gathered from the spatial-order planes x[b,d] / dy[b,d] with the
 // direction's addressing, and du is accumulated (red.global.add) into the spatial-order fp32 plane dx[b,d]
 // — CrossMerge.backward and CrossScan.backward as load / store addressing.  ddelta, dB, dC stay in scan order.
-template <typename in_t, typename out_t, int T, int NW, int SB, int MINB, bool CROSS, bool DIRECT_RED>
+template <typename in_t, typename out_t, int T, int NW, int SB, int MINB, bool CROSS, int NSB_CT>
 __global__ void __launch_bounds__(NW * kWarp, MINB)
 scan_bwd_kernel(const ss2d_scan_bwd_params pb, const int tiles_per_group, const BwdFlags fl, const CrossInfo xinfo) {
     using FT = BCTile<in_t, T, SB>;
@@ -44,13 +157,16 @@ scan_bwd_kernel(const ss2d_scan_bwd_params pb, const int tiles_per_group, const 
     constexpr int chunk = FT::chunk;
     constexpr int NT = NW * kWarp;
     constexpr int ckpt_per_chunk = chunk / SS2D_CKPT_STEPS;
+    constexpr int stage_row = RLf::row_bytes;
     static_assert(chunk % SS2D_CKPT_STEPS == 0, "chunk must be a multiple of the checkpoint spacing");
+    static_assert(2 * (chunk / 4) <= NT, "one reduction task per thread");
     extern __shared__ __align__(16) unsigned char smem[];
     const ss2d_scan_fwd_params &p = pb.f;
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int N = (int)p.dstate;
-    const int Npad = (N + 3) & ~3;
+    const int NS = NSB_CT > 0 ? NSB_CT / 4 : ((N + 3) & ~3);
+    const int nsb_rt = NS * 4;
     const int64_t L = p.seqlen;
     const int per_g = (int)(p.dim / p.ngroups);
     const int tile = blockIdx.x % tiles_per_group;
@@ -63,11 +179,19 @@ scan_bwd_kernel(const ss2d_scan_bwd_params pb, const int tiles_per_group, const 
     // ---- shared memory carve-up ----
     unsigned char *tiles = smem;                                             // 2 x B/C tile (ping-pong)
     unsigned char *stage = smem + 2 * FT::tile_bytes;                        // [NW][2][padded chunk] fp32
-    constexpr int stage_row = RLf::row_bytes;
-    float *sA2 = reinterpret_cast<float *>(stage + NW * 2 * stage_row);      // A*log2e
-    float *sHin = sA2 + NW * Npad;                                           // h entering the current chunk
-    float *sDx = sHin + NW * Npad;                                           // dx carry from the chunk to the right
-    float *sdA = sDx + NW * Npad;                                            // [NW][N][32] per-lane dA partials
+    float *wsm = reinterpret_cast<float *>(stage + NW * 2 * stage_row) + warp * 3 * NS;  // [A2 | Hin | Dx] of this warp
+    float *sA2 = wsm, *sHin = wsm + NS, *sDx = wsm + 2 * NS;
+    float *sdA_all = reinterpret_cast<float *>(stage + NW * 2 * stage_row) + NW * 3 * NS;
+    float *sdA = sdA_all + warp * N * kWarp;                                 // [N][32] per-lane dA partials
+    const uint32_t tiles_addr = smem_u32(tiles) + RL::lane_unit(lane) * 16;
+    const uint32_t wsm_addr = smem_u32(wsm);
+    const uint32_t da_addr = smem_u32(sdA) + lane * 4;
+    const uint32_t st_addr = smem_u32(stage) + warp * 2 * stage_row + RLf::lane_unit(lane) * 16;
+    // cross-channel reduction: thread `task` sums one 16-byte piece of dB (tasks 0..chunk/4-1) or dC over the NW warps
+    const int task = threadIdx.x;
+    const bool reducer = task < 2 * (chunk / 4);
+    const int which = task / (chunk / 4), piece = task % (chunk / 4);
+    const uint32_t rd_addr = smem_u32(stage) + which * stage_row + RLf::unit_of_piece(piece) * 16;
 
     const int64_t cu = CROSS ? (active ? c_local : per_g - 1) : c;  // row of u / dout / du: d in fused mode
     const in_t *u_row = reinterpret_cast<const in_t *>(p.u) + b * p.u_bstride + cu * p.u_dstride;
@@ -82,18 +206,17 @@ scan_bwd_kernel(const ss2d_scan_bwd_params pb, const int tiles_per_group, const 
     float *dx_plane = CROSS ? reinterpret_cast<float *>(pb.du) + ((int64_t)b * per_g + cu) * L : nullptr;
     in_t *dd_row = reinterpret_cast<in_t *>(pb.ddelta) + row;
     in_t *dz_row = pb.dz ? reinterpret_cast<in_t *>(pb.dz) + row : nullptr;
-    float *dBg = pb.dB + ((int64_t)b * p.ngroups + g) * N * L;
-    float *dCg = pb.dC + ((int64_t)b * p.ngroups + g) * N * L;
+    float *red_base = (which ? pb.dC : pb.dB) + ((int64_t)b * p.ngroups + g) * N * L + (int64_t)piece * 4;
     const float Dv = p.D ? p.D[c] : 0.f;
     const float bias = p.delta_bias ? p.delta_bias[c] : 0.f;
     const int n_fine = (int)((L + SS2D_CKPT_STEPS - 1) / SS2D_CKPT_STEPS);
     const float *ck_row = p.ckpt ? p.ckpt + ((int64_t)b * p.dim + c) * n_fine * N : nullptr;
 
     for (int n = lane; n < N; n += kWarp) {
-        sA2[warp * Npad + n] = p.A[c * N + n] * kLog2e;
-        sDx[warp * Npad + n] = 0.f;
+        sA2[n] = p.A[c * N + n] * kLog2e;
+        sDx[n] = 0.f;
     }
-    for (int i = lane; i < N * kWarp; i += kWarp) sdA[warp * N * kWarp + i] = 0.f;
+    for (int i = lane; i < N * kWarp; i += kWarp) sdA[i] = 0.f;
 
     const int n_sb = (N + SB - 1) / SB;
     const int n_chunks = (int)((L + chunk - 1) / chunk);
@@ -107,13 +230,13 @@ scan_bwd_kernel(const ss2d_scan_bwd_params pb, const int tiles_per_group, const 
     float dl_first_right = 0.f;  // dl at the first step of the chunk to the right (0 past the end: a = 1)
     float dD_acc = 0.f, dbias_acc = 0.f;
 
+    int ci = n_chunks - 1, sb = 0;
     for (int q = 0; q < Q; ++q) {
-        const int ci = n_chunks - 1 - q / n_sb, sb = q % n_sb;
         const int64_t t0 = (int64_t)ci * chunk;
         cp_async_wait<0>();
         __syncthreads();
         if (q + 1 < Q) {
-            const int ci1 = n_chunks - 1 - (q + 1) / n_sb, sb1 = (q + 1) % n_sb;
+            const int sb1 = sb + 1 == n_sb ? 0 : sb + 1, ci1 = sb + 1 == n_sb ? ci - 1 : ci;
             stage_bc<in_t, T, SB, NT>(tiles + ((q + 1) & 1) * FT::tile_bytes, Bg, Cg, p.B_nstride, p.C_nstride,
                                       sb1 * SB, N, (int64_t)ci1 * chunk, L, fl.vec_bc);
             cp_async_commit();
@@ -161,114 +284,16 @@ scan_bwd_kernel(const ss2d_scan_bwd_params pb, const int tiles_per_group, const 
             // h entering this chunk, from the forward's fine checkpoints
             __syncwarp();
             for (int n = lane; n < N; n += kWarp)
-                sHin[warp * Npad + n] = (ci > 0 && ck_row) ? ck_row[((int64_t)ci * ckpt_per_chunk - 1) * N + n] : 0.f;
+                sHin[n] = (ci > 0 && ck_row) ? ck_row[((int64_t)ci * ckpt_per_chunk - 1) * N + n] : 0.f;
             __syncwarp();
         }
-        const unsigned char *buf = tiles + (q & 1) * FT::tile_bytes;
-        const int n_here = min(SB, N - sb * SB);
-#pragma unroll 1
-        for (int r = 0; r < n_here; ++r) {
-            const int n = sb * SB + r;
-            const float A2 = sA2[warp * Npad + n];
-            const float An = A2 * (1.f / kLog2e);
-            float a[T], hv[T], Bv[T], Cv[T];
-            lds_block<in_t, T>(buf + r * RL::row_bytes, lane, Bv);
-#pragma unroll
-            float bb[T];
-#pragma unroll
-            for (int i = 0; i < T; ++i) { a[i] = ex2(dl[i] * A2); bb[i] = du[i] * Bv[i]; }
-            // ---- prefix recurrence: pass 1, warp scan, pass 2 (materialise h) ----
-            float H = bb[0];
-#pragma unroll
-            for (int i = 1; i < T; ++i) H = fmaf(a[i], H, bb[i]);
-            float P = ex2(A2 * dsum);
-            warp_scan_inclusive(P, H, lane);
-            float Pe = __shfl_up_sync(0xffffffffu, P, 1), He = __shfl_up_sync(0xffffffffu, H, 1);
-            if (lane == 0) { Pe = 1.f; He = 0.f; }
-            float h = fmaf(Pe, sHin[warp * Npad + n], He);
-#pragma unroll
-            for (int i = 0; i < T; ++i) { h = fmaf(a[i], h, bb[i]); hv[i] = h; }
-            // ---- suffix recurrence on (a_{t+1}, dout_t C_t) ----
-            lds_block<in_t, T>(buf + (SB + r) * RL::row_bytes, lane, Cv);
-#pragma unroll
-            for (int i = 0; i < T; ++i) Cv[i] *= go[i];  // g_t = dout_t C_t
-            const float a_last = ex2(A2 * dlnext);  // a at the step following this lane's block
-            float R = Cv[T - 1];
-#pragma unroll
-            for (int i = T - 2; i >= 0; --i) R = fmaf(a[i + 1], R, Cv[i]);
-            float Qp = ex2(A2 * qsum);
-            warp_rscan_inclusive(Qp, R, lane);
-            float Qe = __shfl_down_sync(0xffffffffu, Qp, 1), Re = __shfl_down_sync(0xffffffffu, R, 1);
-            if (lane == 31) { Qe = 1.f; Re = 0.f; }
-            const float carry = sDx[warp * Npad + n];
-            float dx = fmaf(Qe, carry, Re);  // dx at the first step right of this lane's block
-            // ---- gradients, walking the block right to left ----
-            float dBv[T], dCv[T];
-            float dA_acc = 0.f;
-#pragma unroll
-            for (int i = T - 1; i >= 0; --i) {
-                const float an = i == T - 1 ? a_last : a[i + 1];
-                dx = fmaf(an, dx, Cv[i]);
-                dCv[i] = go[i] * hv[i];
-                dBv[i] = dx * du[i];
-                s[i] = fmaf(dx, Bv[i], s[i]);
-                const float pq = dx * (hv[i] - bb[i]);  // dx_t * a_t h_{t-1}
-                w[i] = fmaf(An, pq, w[i]);
-                dA_acc = fmaf(dl[i], pq, dA_acc);
-            }
-            if (lane == 0) sDx[warp * Npad + n] = dx;  // dx at this chunk's first step -> carry for the left chunk
-            sdA[(warp * N + n) * kWarp + lane] += dA_acc;
-            if constexpr (DIRECT_RED) {
-                // ---- dB/dC: every warp adds its channel's contribution straight into L2 (red.global.add.v4) ----
-                if (active) {
-                    float *dB_dst = dBg + (int64_t)n * L + tl, *dC_dst = dCg + (int64_t)n * L + tl;
-                    if (fl.vec_dbc && valid >= T) {
-#pragma unroll
-                        for (int i = 0; i < T; i += 4) {
-                            red_add_v4(dB_dst + i, dBv[i], dBv[i + 1], dBv[i + 2], dBv[i + 3]);
-                            red_add_v4(dC_dst + i, dCv[i], dCv[i + 1], dCv[i + 2], dCv[i + 3]);
-                        }
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < T; ++i)
-                            if (i < valid) { red_add_f32(dB_dst + i, dBv[i]); red_add_f32(dC_dst + i, dCv[i]); }
-                    }
-                }
-            } else {
-            // ---- dB/dC: reduce over the CTA's channels, then one vector reduction per 4 steps ----
-            if (!active) {
-#pragma unroll
-                for (int i = 0; i < T; ++i) { dBv[i] = 0.f; dCv[i] = 0.f; }
-            }
-            {
-                uint4 *dstB = reinterpret_cast<uint4 *>(stage + (warp * 2 + 0) * stage_row) + RLf::lane_unit(lane);
-                uint4 *dstC = reinterpret_cast<uint4 *>(stage + (warp * 2 + 1) * stage_row) + RLf::lane_unit(lane);
-#pragma unroll
-                for (int i = 0; i < T / 4; ++i) { dstB[i] = pack16<float>(&dBv[4 * i]); dstC[i] = pack16<float>(&dCv[4 * i]); }
-            }
-            __syncthreads();
-            for (int task = threadIdx.x; task < 2 * (chunk / 4); task += NT) {
-                const int which = task / (chunk / 4), piece = task % (chunk / 4);
-                const int unit = RLf::unit_of_piece(piece);
-                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-                for (int ww = 0; ww < NW; ++ww) {
-                    const float4 v = reinterpret_cast<const float4 *>(stage + (ww * 2 + which) * stage_row)[unit];
-                    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
-                }
-                const int64_t t = t0 + (int64_t)piece * 4;
-                float *dst = (which ? dCg : dBg) + (int64_t)n * L + t;
-                if (fl.vec_dbc && t + 4 <= L) {
-                    red_add_v4(dst, acc.x, acc.y, acc.z, acc.w);
-                } else {
-                    if (t + 0 < L) atomicAdd(dst + 0, acc.x);
-                    if (t + 1 < L) atomicAdd(dst + 1, acc.y);
-                    if (t + 2 < L) atomicAdd(dst + 2, acc.z);
-                    if (t + 3 < L) atomicAdd(dst + 3, acc.w);
-                }
-            }
-            __syncthreads();
-            }
+        {
+            const uint32_t bc = tiles_addr + (q & 1) * FT::tile_bytes;
+            const int64_t tp = t0 + (int64_t)piece * 4;
+            bwd_block<in_t, T, SB, NSB_CT, NW>(bc, wsm_addr + sb * SB * 4, nsb_rt, da_addr + sb * SB * 128, st_addr, rd_addr,
+                                               lane, active, reducer, red_base + (int64_t)sb * SB * L + t0, L, fl.vec_dbc,
+                                               (int)min((int64_t)4, L - tp), dl, du, go, s, w, dsum, qsum, dlnext,
+                                               min(SB, N - sb * SB));
         }
         if (sb == n_sb - 1) {  // chunk finished: du, ddelta
             float ddl[T];
@@ -288,12 +313,13 @@ scan_bwd_kernel(const ss2d_scan_bwd_params pb, const int tiles_per_group, const 
             }
             dl_first_right = __shfl_sync(0xffffffffu, dl[0], 0);
         }
+        if (++sb == n_sb) { sb = 0; --ci; }
     }
     // ---- per-channel reductions over time (and atomically over batch) ----
     __syncwarp();
     if (active) {
         for (int n = 0; n < N; ++n) {
-            float v = sdA[(warp * N + n) * kWarp + lane];
+            float v = sdA[n * kWarp + lane];
 #pragma unroll
             for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
             if (lane == 0) atomicAdd(pb.dA + c * N + n, v);
@@ -312,16 +338,18 @@ scan_bwd_kernel(const ss2d_scan_bwd_params pb, const int tiles_per_group, const 
 
 static inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
-template <typename in_t, typename out_t, int T, int NW, int MINB, bool CROSS = false, bool DIRECT_RED = false>
+template <typename in_t, typename out_t, int T, int NW, int MINB, bool CROSS = false>
 static int launch_bwd(const ss2d_scan_bwd_params &pb, cudaStream_t stream, CrossInfo xinfo = CrossInfo{0, 0}) {
     constexpr int SB = 8;
     using FT = BCTile<in_t, T, SB>;
     const ss2d_scan_fwd_params &p = pb.f;
     const int per_g = (int)(p.dim / p.ngroups);
     const int tiles = (per_g + NW - 1) / NW;
-    const int N = (int)p.dstate, Npad = (N + 3) & ~3;
+    const int N = (int)p.dstate;
+    const bool small_n = N <= 16;
+    const int NS = small_n ? 16 : ((N + 3) & ~3);
     const size_t smem = 2 * FT::tile_bytes + NW * 2 * RowLayout<float, T>::row_bytes +
-                        (3 * NW * Npad + NW * N * kWarp) * sizeof(float);
+                        ((size_t)3 * NW * NS + (size_t)NW * N * kWarp) * sizeof(float);
     const int64_t ei = sizeof(in_t), eo = sizeof(out_t);
     BwdFlags fl;
     fl.vec_u = aligned16(p.u) && (p.u_bstride * ei) % 16 == 0 && (p.u_dstride * ei) % 16 == 0;
@@ -336,12 +364,15 @@ static int launch_bwd(const ss2d_scan_bwd_params &pb, cudaStream_t stream, Cross
     // du / ddelta / dz rows are contiguous (batch, dim, L)
     fl.vec_grad = aligned16(pb.du) && aligned16(pb.ddelta) && (!pb.dz || aligned16(pb.dz)) && (p.seqlen * ei) % 16 == 0;
     if (CROSS) fl.vec_dbc = fl.vec_dbc && aligned16(pb.du);  // dx plane rows are L floats: 16-byte aligned iff L % 4 == 0
-    auto kern = scan_bwd_kernel<in_t, out_t, T, NW, SB, MINB, CROSS, DIRECT_RED>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
     const int64_t grid = p.batch * p.ngroups * tiles;
-    kern<<<(unsigned)grid, NW * kWarp, smem, stream>>>(pb, tiles, fl, xinfo);
-    return (int)cudaGetLastError();
+    auto go = [&](auto kern) -> int {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        kern<<<(unsigned)grid, NW * kWarp, smem, stream>>>(pb, tiles, fl, xinfo);
+        return (int)cudaGetLastError();
+    };
+    if (small_n) return go(scan_bwd_kernel<in_t, out_t, T, NW, SB, MINB, CROSS, 64>);
+    return go(scan_bwd_kernel<in_t, out_t, T, NW, SB, MINB, CROSS, 0>);
 }
 
 }  // namespace ss2d
@@ -371,20 +402,6 @@ extern "C" int ss2d_selective_scan_bwd(const ss2d_scan_bwd_params *pp, void *str
     }
     using namespace ss2d;
     constexpr int T = SS2D_BWD_T, NW = SS2D_BWD_NW, MINB = SS2D_BWD_MINB;
-#ifdef SS2D_TUNE  // development knob: SS2D_BWD_CFG=TxNWxMINBx{s|d} (s = smem-staged dB/dC reduction, d = direct RED)
-    if (p.in_dtype == SS2D_F32) {
-        const char *cfg = getenv("SS2D_BWD_CFG");
-        if (cfg) {
-            if (!strcmp(cfg, "8x8x2xd")) return launch_bwd<float, float, 8, 8, 2, false, true>(pb, s);
-            if (!strcmp(cfg, "8x8x3xd")) return launch_bwd<float, float, 8, 8, 3, false, true>(pb, s);
-            if (!strcmp(cfg, "8x4x4xd")) return launch_bwd<float, float, 8, 4, 4, false, true>(pb, s);
-            if (!strcmp(cfg, "8x16x1xs")) return launch_bwd<float, float, 8, 16, 1, false, false>(pb, s);
-            if (!strcmp(cfg, "8x16x1xd")) return launch_bwd<float, float, 8, 16, 1, false, true>(pb, s);
-            if (!strcmp(cfg, "16x8x1xs")) return launch_bwd<float, float, 16, 8, 1, false, false>(pb, s);
-            if (!strcmp(cfg, "16x8x1xd")) return launch_bwd<float, float, 16, 8, 1, false, true>(pb, s);
-        }
-    }
-#endif
     switch (p.in_dtype) {
         case SS2D_F32: return launch_bwd<float, float, T, NW, MINB>(pb, s);
         case SS2D_F16:
