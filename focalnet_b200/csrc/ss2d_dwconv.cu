@@ -49,33 +49,60 @@ __device__ __forceinline__ void dw_stage(float (*tile)[kPw + 2][kCw], const floa
     }
 }
 
+// Forward: one block = 32 channels x 32 pixels x kTh rows.  The kTh+2 input rows are staged once (row re-read
+// factor (kTh+2)/kTh instead of 3), every thread produces 4*kTh outputs, and the (channel, pixel) tiles are turned
+// through shared memory so that the channels-first stores are 128-byte coalesced.
+constexpr int kTh = 4;
 __global__ void __launch_bounds__(kCw *kTy) dwconv_silu_fwd_kernel(const float *__restrict__ xin, const float *__restrict__ weight,
                                                                   const float *__restrict__ bias, float *__restrict__ out,
                                                                   const DwGeom g) {
-    __shared__ float tin[3][kPw + 2][kCw];
-    __shared__ float tout[kCw][kPw + 1];
-    int b, h, w0, c0;
-    dw_decode(g, b, h, w0, c0);
+    __shared__ float tin[kTh + 2][kPw + 2][kCw];
+    __shared__ float tout[kTh][kCw][kPw + 1];
+    int id = blockIdx.x;
+    const int c0 = (id % g.tiles_c) * kCw; id /= g.tiles_c;
+    const int w0 = (id % g.tiles_w) * kPw; id /= g.tiles_w;
+    const int tiles_h = (g.H + kTh - 1) / kTh;
+    const int h0 = (id % tiles_h) * kTh, b = id / tiles_h;
     const int tx = threadIdx.x, ty = threadIdx.y;
     const int c = c0 + tx;
     float wgt[9];
 #pragma unroll
     for (int q = 0; q < 9; ++q) wgt[q] = c < g.C ? weight[c * 9 + q] : 0.f;
     const float bv = (bias && c < g.C) ? bias[c] : 0.f;
-    dw_stage(tin, xin, g.cstride, g, b, h, w0, c0);
-    __syncthreads();
-    for (int wi = ty; wi < kPw; wi += kTy) {
-        float s = bv;
 #pragma unroll
-        for (int r = 0; r < 3; ++r)
-#pragma unroll
-            for (int j = 0; j < 3; ++j) s = fmaf(wgt[r * 3 + j], tin[r][wi + j][tx], s);
-        tout[tx][wi] = s * sigmoidf_fast(s);
+    for (int r = 0; r < kTh + 2; ++r) {
+        const int hh = h0 - 1 + r;
+        for (int wi = ty; wi < kPw + 2; wi += kTy) {
+            const int ww = w0 - 1 + wi;
+            float v = 0.f;
+            if (hh >= 0 && hh < g.H && ww >= 0 && ww < g.W && c < g.C)
+                v = __ldg(xin + (((int64_t)b * g.H + hh) * g.W + ww) * g.cstride + c);
+            tin[r][wi][tx] = v;
+        }
     }
     __syncthreads();
-    for (int cc = ty; cc < kCw; cc += kTy) {  // lanes now walk pixels: contiguous in (B,C,H,W)
-        const int w = w0 + tx;
-        if (c0 + cc < g.C && w < g.W) out[(((int64_t)b * g.C + c0 + cc) * g.H + h) * g.W + w] = tout[cc][tx];
+#pragma unroll
+    for (int hr = 0; hr < kTh; ++hr) {
+#pragma unroll
+        for (int k = 0; k < kPw / kTy; ++k) {
+            const int wi = ty + k * kTy;
+            float s = bv;
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+#pragma unroll
+                for (int j = 0; j < 3; ++j) s = fmaf(wgt[r * 3 + j], tin[hr + r][wi + j][tx], s);
+            tout[hr][tx][wi] = s * sigmoidf_fast(s);
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int hr = 0; hr < kTh; ++hr) {
+        const int h = h0 + hr;
+#pragma unroll
+        for (int k = 0; k < kCw / kTy; ++k) {  // lanes now walk pixels: contiguous in (B,C,H,W)
+            const int cc = ty + k * kTy, w = w0 + tx;
+            if (h < g.H && c0 + cc < g.C && w < g.W) out[(((int64_t)b * g.C + c0 + cc) * g.H + h) * g.W + w] = tout[hr][cc][tx];
+        }
     }
 }
 
@@ -178,7 +205,7 @@ extern "C" int ss2d_dwconv_silu_fwd(const float *xin, int64_t cstride, const flo
     if (!xin || !weight || !out) return SS2D_EINVAL;
     DwGeom g;
     if (int rc = dw_geom(g, cstride, batch, C, H, W)) return rc;
-    const unsigned grid = (unsigned)((int64_t)g.tiles_w * g.tiles_c * H * batch);
+    const unsigned grid = (unsigned)((int64_t)g.tiles_w * g.tiles_c * ((H + kTh - 1) / kTh) * batch);
     dwconv_silu_fwd_kernel<<<grid, dim3(kCw, kTy), 0, reinterpret_cast<cudaStream_t>(stream)>>>(xin, weight, bias, out, g);
     return (int)cudaGetLastError();
 }

@@ -338,9 +338,8 @@ scan_bwd_kernel(const ss2d_scan_bwd_params pb, const int tiles_per_group, const 
 
 static inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
-template <typename in_t, typename out_t, int T, int NW, int MINB, bool CROSS = false>
+template <typename in_t, typename out_t, int T, int NW, int MINB, bool CROSS = false, int SB = 8>
 static int launch_bwd(const ss2d_scan_bwd_params &pb, cudaStream_t stream, CrossInfo xinfo = CrossInfo{0, 0}) {
-    constexpr int SB = 8;
     using FT = BCTile<in_t, T, SB>;
     const ss2d_scan_fwd_params &p = pb.f;
     const int per_g = (int)(p.dim / p.ngroups);
@@ -402,6 +401,17 @@ extern "C" int ss2d_selective_scan_bwd(const ss2d_scan_bwd_params *pp, void *str
     }
     using namespace ss2d;
     constexpr int T = SS2D_BWD_T, NW = SS2D_BWD_NW, MINB = SS2D_BWD_MINB;
+#ifdef SS2D_TUNE  // development knob: SS2D_BWD_CFG=TxNWxMINBxSB
+    if (p.in_dtype == SS2D_F32) {
+        const char *cfg = getenv("SS2D_BWD_CFG");
+        if (cfg) {
+            if (!strcmp(cfg, "16x12x1x6")) return launch_bwd<float, float, 16, 12, 1, false, 6>(pb, s);
+            if (!strcmp(cfg, "16x8x1x8")) return launch_bwd<float, float, 16, 8, 1, false, 8>(pb, s);
+            if (!strcmp(cfg, "16x16x1x8")) return launch_bwd<float, float, 16, 16, 1, false, 8>(pb, s);
+            if (!strcmp(cfg, "8x16x1x8")) return launch_bwd<float, float, 8, 16, 1, false, 8>(pb, s);
+        }
+    }
+#endif
     switch (p.in_dtype) {
         case SS2D_F32: return launch_bwd<float, float, T, NW, MINB>(pb, s);
         case SS2D_F16:

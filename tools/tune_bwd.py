@@ -19,7 +19,7 @@ args = (d["u"], d["delta"], d["A"], d["B"], d["C"], d["D"], d["delta_bias"])
 out, x, ckpt, _ = scan_fwd(*args, True, 1, True)
 f = lambda: scan_bwd(*args, d["dout"], x, True, 1, ckpt=ckpt)
 base = None
-for cfg in ["", "8x8x2xd", "8x8x3xd", "8x4x4xd", "8x16x1xs", "8x16x1xd", "16x8x1xs", "16x8x1xd"]:
+for cfg in ["", "16x12x1x6", "16x8x1x8", "16x16x1x8", "8x16x1x8"]:
     if cfg: os.environ["SS2D_BWD_CFG"] = cfg
     g = f()
     if base is None: base = g
