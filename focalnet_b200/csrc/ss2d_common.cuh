@@ -275,22 +275,66 @@ template <typename T, int TT, int OFF> __device__ __forceinline__ void lds_row(u
 
 // ---- the scan combine (a0,b0) o (a1,b1) = (a1 a0, a1 b0 + b1)  (selective_scan_common.h:93-95) ----
 // Inclusive Kogge-Stone scan over the 32 lanes of the block aggregates (P = prod a, H = local h_end).
-__device__ __forceinline__ void warp_scan_inclusive(float &P, float &H, int lane) {
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const float Pp = __shfl_up_sync(0xffffffffu, P, d);
-        const float Hp = __shfl_up_sync(0xffffffffu, H, d);
-        if (lane >= d) { H = fmaf(P, Hp, H); P *= Pp; }
-    }
+// shfl.sync returns an "in range" predicate together with the data, so each round is 2 SHFL + 2 predicated
+// FP instructions with no persistent predicate registers (the backward runs two scans per state and was
+// spilling its ten `lane >= d` predicates into a general register).
+template <int D> __device__ __forceinline__ void scan_round_up(float &P, float &H) {
+    asm(
+        "{\n\t"
+        ".reg .pred q;\n\t"
+        ".reg .f32 hp, pp;\n\t"
+        "shfl.sync.up.b32 hp|q, %0, %2, 0, 0xffffffff;\n\t"
+        "shfl.sync.up.b32 pp, %1, %2, 0, 0xffffffff;\n\t"
+        "@q fma.rn.f32 %0, %1, hp, %0;\n\t"
+        "@q mul.f32 %1, %1, pp;\n\t"
+        "}"
+        : "+f"(H), "+f"(P)
+        : "n"(D));
+}
+template <int D> __device__ __forceinline__ void scan_round_down(float &P, float &H) {
+    asm(
+        "{\n\t"
+        ".reg .pred q;\n\t"
+        ".reg .f32 hp, pp;\n\t"
+        "shfl.sync.down.b32 hp|q, %0, %2, 0x1f, 0xffffffff;\n\t"
+        "shfl.sync.down.b32 pp, %1, %2, 0x1f, 0xffffffff;\n\t"
+        "@q fma.rn.f32 %0, %1, hp, %0;\n\t"
+        "@q mul.f32 %1, %1, pp;\n\t"
+        "}"
+        : "+f"(H), "+f"(P)
+        : "n"(D));
+}
+__device__ __forceinline__ void warp_scan_inclusive(float &P, float &H, int /*lane*/) {
+    scan_round_up<1>(P, H); scan_round_up<2>(P, H); scan_round_up<4>(P, H); scan_round_up<8>(P, H); scan_round_up<16>(P, H);
 }
 // Mirror image for the backward's suffix scan: lane j combines with lanes j+d.
-__device__ __forceinline__ void warp_rscan_inclusive(float &P, float &H, int lane) {
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const float Pp = __shfl_down_sync(0xffffffffu, P, d);
-        const float Hp = __shfl_down_sync(0xffffffffu, H, d);
-        if (lane + d < 32) { H = fmaf(P, Hp, H); P *= Pp; }
-    }
+__device__ __forceinline__ void warp_rscan_inclusive(float &P, float &H, int /*lane*/) {
+    scan_round_down<1>(P, H); scan_round_down<2>(P, H); scan_round_down<4>(P, H); scan_round_down<8>(P, H); scan_round_down<16>(P, H);
+}
+// Exclusive neighbour (identity (1, 0) at the warp edge), again with the shuffle's own predicate.
+__device__ __forceinline__ void shift_up1(float P, float H, float &Pe, float &He) {
+    asm(
+        "{\n\t"
+        ".reg .pred q;\n\t"
+        "shfl.sync.up.b32 %0|q, %2, 1, 0, 0xffffffff;\n\t"
+        "shfl.sync.up.b32 %1, %3, 1, 0, 0xffffffff;\n\t"
+        "@!q mov.f32 %0, 0f00000000;\n\t"
+        "@!q mov.f32 %1, 0f3f800000;\n\t"
+        "}"
+        : "=&f"(He), "=&f"(Pe)
+        : "f"(H), "f"(P));
+}
+__device__ __forceinline__ void shift_down1(float P, float H, float &Pe, float &He) {
+    asm(
+        "{\n\t"
+        ".reg .pred q;\n\t"
+        "shfl.sync.down.b32 %0|q, %2, 1, 0x1f, 0xffffffff;\n\t"
+        "shfl.sync.down.b32 %1, %3, 1, 0x1f, 0xffffffff;\n\t"
+        "@!q mov.f32 %0, 0f00000000;\n\t"
+        "@!q mov.f32 %1, 0f3f800000;\n\t"
+        "}"
+        : "=&f"(He), "=&f"(Pe)
+        : "f"(H), "f"(P));
 }
 
 }  // namespace ss2d

@@ -57,8 +57,8 @@ __device__ __forceinline__ void bwd_state(uint32_t bc, uint32_t wa, int nsb_rt, 
     for (int i = 1; i < T; ++i) H = fmaf(a[i], H, bb[i]);
     float P = ex2(A2 * dsum);
     warp_scan_inclusive(P, H, lane);
-    float Pe = __shfl_up_sync(0xffffffffu, P, 1), He = __shfl_up_sync(0xffffffffu, H, 1);
-    if (lane == 0) { Pe = 1.f; He = 0.f; }
+    float Pe, He;
+    shift_up1(P, H, Pe, He);
     const uint32_t hin_addr = wa + (NSB_CT > 0 ? NSB_CT : nsb_rt);
     float h = fmaf(Pe, lds_f32<R * 4>(hin_addr), He);
 #pragma unroll
@@ -73,8 +73,8 @@ __device__ __forceinline__ void bwd_state(uint32_t bc, uint32_t wa, int nsb_rt, 
     for (int i = T - 2; i >= 0; --i) Rr = fmaf(a[i + 1], Rr, Cv[i]);
     float Qp = ex2(A2 * qsum);
     warp_rscan_inclusive(Qp, Rr, lane);
-    float Qe = __shfl_down_sync(0xffffffffu, Qp, 1), Re = __shfl_down_sync(0xffffffffu, Rr, 1);
-    if (lane == 31) { Qe = 1.f; Re = 0.f; }
+    float Qe, Re;
+    shift_down1(Qp, Rr, Qe, Re);
     const uint32_t dx_addr = wa + (NSB_CT > 0 ? 2 * NSB_CT : 2 * nsb_rt);
     float dx = fmaf(Qe, lds_f32<R * 4>(dx_addr), Re);  // dx at the first step right of this lane's block
     // ---- gradients, walking the block right to left ----

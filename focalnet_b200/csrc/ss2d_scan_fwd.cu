@@ -46,8 +46,8 @@ __device__ __forceinline__ void fwd_state(uint32_t bc, uint32_t wa, int nsb_rt, 
     for (int i = 1; i < T; ++i) { hl[i] = fmaf(a[i], hl[i - 1], hl[i]); a[i] *= a[i - 1]; }
     float P = a[T - 1], H = hl[T - 1];
     warp_scan_inclusive(P, H, lane);
-    float Pe = __shfl_up_sync(0xffffffffu, P, 1), He = __shfl_up_sync(0xffffffffu, H, 1);
-    if (lane == 0) { Pe = 1.f; He = 0.f; }
+    float Pe, He;
+    shift_up1(P, H, Pe, He);
     const uint32_t carry_addr = wa + (NSB_CT > 0 ? (1 + SLOTS) * NSB_CT : (1 + SLOTS) * nsb_rt);
     const float hin = fmaf(Pe, lds_f32<R * 4>(carry_addr), He);  // carry = h at the end of the previous chunk
     float Cv[T];
