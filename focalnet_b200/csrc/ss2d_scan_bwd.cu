@@ -37,6 +37,9 @@ struct BwdFlags {
 //   wa   : shared address of this warp's [A*log2e | h entering the chunk | dx carry] arrays (NSB bytes apart)
 //          at the block's first state;  da: this lane's dA partial sums (128 bytes per state)
 //   st   : this lane's slot in the fp32 staging rows of its warp (dB row, then dC row `stage_row` bytes later)
+//   The staging area is double buffered (`par` selects the half): state r's partial sums are reduced by half of the
+//   warps (alternating halves) while everybody already computes state r+1, so there is ONE block barrier per state;
+//   the barrier of state r+1 also proves that every reader of buffer `par` is done before state r+2 refills it.
 template <typename in_t, int T, int SB, int R, int NSB_CT, int NW>
 __device__ __forceinline__ void bwd_state(uint32_t bc, uint32_t wa, int nsb_rt, uint32_t da, uint32_t st, uint32_t rd,
                                           int lane, bool active, bool reducer, float *red_dst, bool red_vec, int red_valid,
@@ -92,7 +95,8 @@ __device__ __forceinline__ void bwd_state(uint32_t bc, uint32_t wa, int nsb_rt, 
         dA_acc = fmaf(dl[i], pq, dA_acc);
     }
     if (lane == 0) sts_f32<R * 4>(dx_addr, dx);  // dx at this chunk's first step -> carry for the left chunk
-    sts_f32<R * 128>(da, lds_f32<R * 128>(da) + dA_acc);
+    dA_acc += __shfl_xor_sync(0xffffffffu, dA_acc, 1);  // lane pairs share one slot: 16 partials per (warp, state)
+    if ((lane & 1) == 0) sts_f32<R * 64>(da, lds_f32<R * 64>(da) + dA_acc);
     // ---- dB/dC: reduce over the CTA's channels in shared memory, then one vector reduction per 4 steps ----
     if (!active) {
 #pragma unroll
@@ -105,7 +109,7 @@ __device__ __forceinline__ void bwd_state(uint32_t bc, uint32_t wa, int nsb_rt, 
         if (i == 2) { sts_v4<32>(st, pack16<float>(&dBv[8])); sts_v4<stage_row + 32>(st, pack16<float>(&dCv[8])); }
         if (i == 3) { sts_v4<48>(st, pack16<float>(&dBv[12])); sts_v4<stage_row + 48>(st, pack16<float>(&dCv[12])); }
     }
-    __syncthreads();
+    __syncthreads();  // the only block barrier of this state
     if (reducer) {
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #define SS2D_ACC(WW)                                                                  \
@@ -127,20 +131,22 @@ __device__ __forceinline__ void bwd_state(uint32_t bc, uint32_t wa, int nsb_rt, 
             if (red_valid > 3) atomicAdd(red_dst + 3, acc.w);
         }
     }
-    __syncthreads();
 }
 
 template <typename in_t, int T, int SB, int NSB_CT, int NW, int R = 0>
-__device__ __forceinline__ void bwd_block(uint32_t bc, uint32_t wa, int nsb_rt, uint32_t da, uint32_t st, uint32_t rd, int lane,
+__device__ __forceinline__ void bwd_block(uint32_t bc, uint32_t wa, int nsb_rt, uint32_t da, uint32_t st, uint32_t st_other,
+                                          uint32_t rd, uint32_t rd_other, int lane,
                                           bool active, bool reducer, float *red_dst, int64_t L, bool red_vec, int red_valid,
                                           const float (&dl)[T], const float (&du)[T], const float (&go)[T], float (&s)[T],
                                           float (&w)[T], float dsum, float qsum, float dlnext, int n_here) {
     if constexpr (R < SB) {
-        if (R < n_here) {  // uniform across the CTA: the barriers inside bwd_state are safe
+        if (R < n_here) {  // uniform across the CTA: the barrier inside bwd_state is safe
             bwd_state<in_t, T, SB, R, NSB_CT, NW>(bc, wa, nsb_rt, da, st, rd, lane, active, reducer, red_dst, red_vec,
                                                  red_valid, dl, du, go, s, w, dsum, qsum, dlnext);
-            bwd_block<in_t, T, SB, NSB_CT, NW, R + 1>(bc, wa, nsb_rt, da, st, rd, lane, active, reducer, red_dst + L, L,
-                                                     red_vec, red_valid, dl, du, go, s, w, dsum, qsum, dlnext, n_here);
+            // next state: other staging half, other half of the warps reduces
+            bwd_block<in_t, T, SB, NSB_CT, NW, R + 1>(bc, wa, nsb_rt, da, st_other, st, rd_other, rd, lane, active,
+                                                     !reducer, red_dst + L, L, red_vec, red_valid, dl, du, go, s, w, dsum,
+                                                     qsum, dlnext, n_here);
         }
     }
 }
@@ -159,7 +165,8 @@ scan_bwd_kernel(const ss2d_scan_bwd_params pb, const int tiles_per_group, const 
     constexpr int ckpt_per_chunk = chunk / SS2D_CKPT_STEPS;
     constexpr int stage_row = RLf::row_bytes;
     static_assert(chunk % SS2D_CKPT_STEPS == 0, "chunk must be a multiple of the checkpoint spacing");
-    static_assert(2 * (chunk / 4) <= NT, "one reduction task per thread");
+    static_assert(2 * (chunk / 4) == NT / 2, "half of the CTA's threads reduce one state: needs T == NW");
+    constexpr int stage_half = NW * 2 * stage_row;  // one staging buffer: [NW][dB row | dC row]
     extern __shared__ __align__(16) unsigned char smem[];
     const ss2d_scan_fwd_params &p = pb.f;
 
@@ -179,18 +186,19 @@ scan_bwd_kernel(const ss2d_scan_bwd_params pb, const int tiles_per_group, const 
     // ---- shared memory carve-up ----
     unsigned char *tiles = smem;                                             // 2 x B/C tile (ping-pong)
     unsigned char *stage = smem + 2 * FT::tile_bytes;                        // [NW][2][padded chunk] fp32
-    float *wsm = reinterpret_cast<float *>(stage + NW * 2 * stage_row) + warp * 3 * NS;  // [A2 | Hin | Dx] of this warp
+    float *wsm = reinterpret_cast<float *>(stage + 2 * stage_half) + warp * 3 * NS;  // [A2 | Hin | Dx] of this warp
     float *sA2 = wsm, *sHin = wsm + NS, *sDx = wsm + 2 * NS;
-    float *sdA_all = reinterpret_cast<float *>(stage + NW * 2 * stage_row) + NW * 3 * NS;
-    float *sdA = sdA_all + warp * N * kWarp;                                 // [N][32] per-lane dA partials
+    float *sdA_all = reinterpret_cast<float *>(stage + 2 * stage_half) + NW * 3 * NS;
+    float *sdA = sdA_all + warp * N * 16;                                    // [N][16] lane-pair dA partials
     const uint32_t tiles_addr = smem_u32(tiles) + RL::lane_unit(lane) * 16;
     const uint32_t wsm_addr = smem_u32(wsm);
-    const uint32_t da_addr = smem_u32(sdA) + lane * 4;
+    const uint32_t da_addr = smem_u32(sdA) + (lane >> 1) * 4;
     const uint32_t st_addr = smem_u32(stage) + warp * 2 * stage_row + RLf::lane_unit(lane) * 16;
     // cross-channel reduction: thread `task` sums one 16-byte piece of dB (tasks 0..chunk/4-1) or dC over the NW warps
-    const int task = threadIdx.x;
-    const bool reducer = task < 2 * (chunk / 4);
+    // (the reducing half of the CTA alternates from state to state)
+    const int task = threadIdx.x % (NT / 2);
     const int which = task / (chunk / 4), piece = task % (chunk / 4);
+    int par = 0;  // staging buffer / reducing half of the next state
     const uint32_t rd_addr = smem_u32(stage) + which * stage_row + RLf::unit_of_piece(piece) * 16;
 
     const int64_t cu = CROSS ? (active ? c_local : per_g - 1) : c;  // row of u / dout / du: d in fused mode
@@ -216,7 +224,7 @@ scan_bwd_kernel(const ss2d_scan_bwd_params pb, const int tiles_per_group, const 
         sA2[n] = p.A[c * N + n] * kLog2e;
         sDx[n] = 0.f;
     }
-    for (int i = lane; i < N * kWarp; i += kWarp) sdA[i] = 0.f;
+    for (int i = lane; i < N * 16; i += kWarp) sdA[i] = 0.f;
 
     const int n_sb = (N + SB - 1) / SB;
     const int n_chunks = (int)((L + chunk - 1) / chunk);
@@ -290,10 +298,14 @@ scan_bwd_kernel(const ss2d_scan_bwd_params pb, const int tiles_per_group, const 
         {
             const uint32_t bc = tiles_addr + (q & 1) * FT::tile_bytes;
             const int64_t tp = t0 + (int64_t)piece * 4;
-            bwd_block<in_t, T, SB, NSB_CT, NW>(bc, wsm_addr + sb * SB * 4, nsb_rt, da_addr + sb * SB * 128, st_addr, rd_addr,
-                                               lane, active, reducer, red_base + (int64_t)sb * SB * L + t0, L, fl.vec_dbc,
-                                               (int)min((int64_t)4, L - tp), dl, du, go, s, w, dsum, qsum, dlnext,
-                                               min(SB, N - sb * SB));
+            const int n_here = min(SB, N - sb * SB);
+            const uint32_t st0 = st_addr + par * stage_half, st1 = st_addr + (par ^ 1) * stage_half;
+            const uint32_t rd0 = rd_addr + par * stage_half, rd1 = rd_addr + (par ^ 1) * stage_half;
+            bwd_block<in_t, T, SB, NSB_CT, NW>(bc, wsm_addr + sb * SB * 4, nsb_rt, da_addr + sb * SB * 64, st0, st1, rd0, rd1,
+                                               lane, active, (warp < NW / 2) == (par == 0),
+                                               red_base + (int64_t)sb * SB * L + t0, L, fl.vec_dbc,
+                                               (int)min((int64_t)4, L - tp), dl, du, go, s, w, dsum, qsum, dlnext, n_here);
+            par ^= n_here & 1;
         }
         if (sb == n_sb - 1) {  // chunk finished: du, ddelta
             float ddl[T];
@@ -319,9 +331,9 @@ scan_bwd_kernel(const ss2d_scan_bwd_params pb, const int tiles_per_group, const 
     __syncwarp();
     if (active) {
         for (int n = 0; n < N; ++n) {
-            float v = sdA[n * kWarp + lane];
+            float v = lane < 16 ? sdA[n * 16 + lane] : 0.f;
 #pragma unroll
-            for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+            for (int d = 8; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
             if (lane == 0) atomicAdd(pb.dA + c * N + n, v);
         }
 #pragma unroll
@@ -347,8 +359,8 @@ static int launch_bwd(const ss2d_scan_bwd_params &pb, cudaStream_t stream, Cross
     const int N = (int)p.dstate;
     const bool small_n = N <= 16;
     const int NS = small_n ? 16 : ((N + 3) & ~3);
-    const size_t smem = 2 * FT::tile_bytes + NW * 2 * RowLayout<float, T>::row_bytes +
-                        ((size_t)3 * NW * NS + (size_t)NW * N * kWarp) * sizeof(float);
+    const size_t smem = 2 * FT::tile_bytes + 2 * (size_t)NW * 2 * RowLayout<float, T>::row_bytes +
+                        ((size_t)3 * NW * NS + (size_t)NW * N * 16) * sizeof(float);
     const int64_t ei = sizeof(in_t), eo = sizeof(out_t);
     BwdFlags fl;
     fl.vec_u = aligned16(p.u) && (p.u_bstride * ei) % 16 == 0 && (p.u_dstride * ei) % 16 == 0;
@@ -401,17 +413,6 @@ extern "C" int ss2d_selective_scan_bwd(const ss2d_scan_bwd_params *pp, void *str
     }
     using namespace ss2d;
     constexpr int T = SS2D_BWD_T, NW = SS2D_BWD_NW, MINB = SS2D_BWD_MINB;
-#ifdef SS2D_TUNE  // development knob: SS2D_BWD_CFG=TxNWxMINBxSB
-    if (p.in_dtype == SS2D_F32) {
-        const char *cfg = getenv("SS2D_BWD_CFG");
-        if (cfg) {
-            if (!strcmp(cfg, "16x12x1x6")) return launch_bwd<float, float, 16, 12, 1, false, 6>(pb, s);
-            if (!strcmp(cfg, "16x8x1x8")) return launch_bwd<float, float, 16, 8, 1, false, 8>(pb, s);
-            if (!strcmp(cfg, "16x16x1x8")) return launch_bwd<float, float, 16, 16, 1, false, 8>(pb, s);
-            if (!strcmp(cfg, "8x16x1x8")) return launch_bwd<float, float, 8, 16, 1, false, 8>(pb, s);
-        }
-    }
-#endif
     switch (p.in_dtype) {
         case SS2D_F32: return launch_bwd<float, float, T, NW, MINB>(pb, s);
         case SS2D_F16:
