@@ -139,3 +139,51 @@ def test_errors_match_reference_behaviour():
         scan_fwd(d["u"], d["delta"].half(), d["A"], d["B"], d["C"])
     with pytest.raises(RuntimeError):   # CPU tensors: no CPU path
         scan_fwd(d["u"].cpu(), d["delta"].cpu(), d["A"].cpu(), d["B"].cpu(), d["C"].cpu())
+
+
+def test_strided_operands_are_honoured():
+    """Batch / channel strides are arbitrary in the reference (only the last stride must be 1,
+    selective_scan_oflex.cpp:181-182,198-200): feed slices of larger buffers and a (batch, L, dim)-major u."""
+    from focalnet_b200 import scan_bwd, scan_fwd
+    from oracle import ss2d_oracle as orc
+    B, dim, N, L, G = 2, 12, 16, 530, 2
+    d = make_scan_inputs(B, dim, N, L, G, seed=17)
+    big_u = torch.zeros(B, dim + 3, L + 8, device="cuda")
+    big_u[:, 1:dim + 1, 4:L + 4] = d["u"]
+    u = big_u[:, 1:dim + 1, 4:L + 4]                               # row starts not 16-byte aligned -> scalar path
+    delta = torch.zeros(B, 2 * dim, L, device="cuda")[:, ::2]      # channel stride 2*L
+    delta.copy_(d["delta"])
+    Bbig = torch.zeros(B, G, N + 2, L, device="cuda")
+    Bbig[:, :, 1:N + 1] = d["B"]
+    Bm = Bbig[:, :, 1:N + 1]
+    Cm = d["C"].transpose(0, 1).contiguous().transpose(0, 1)       # (G, B, N, L) storage
+    assert not u.is_contiguous() and not delta.is_contiguous() and not Bm.is_contiguous() and not Cm.is_contiguous()
+    out, x, ckpt, _ = scan_fwd(u, delta, d["A"], Bm, Cm, d["D"], d["delta_bias"], True)
+    g = scan_bwd(u, delta, d["A"], Bm, Cm, d["D"], d["delta_bias"], d["dout"], x, True)
+    f = orc.scan_fwd(d["u"], d["delta"], d["A"], d["B"], d["C"], d["D"], None, d["delta_bias"], True)
+    b = orc.scan_bwd(d["u"], d["delta"], d["A"], d["B"], d["C"], d["D"], None, d["delta_bias"], d["dout"], True)
+    assert rel_err(out, f["out"]) < 1e-3
+    for k, v in zip(GRADS[:7], g):
+        assert rel_err(v, b[k]) < 1e-3, k
+
+
+def test_large_model_like_shape_properties():
+    """At the full microbench size the oracle is too slow to run in a unit test; check size-independent properties:
+    (1) batch rows are independent (scan of a batch slice == slice of the scan), (2) linearity of out in u for the
+    D=0 system, (3) sharding the channel axis by groups gives the same result, (4) determinism of the forward."""
+    from focalnet_b200 import scan_fwd
+    B, dim, N, L, G = 8, 768, 16, 4096, 4
+    d = make_scan_inputs(B, dim, N, L, G, seed=2, model_like=True)
+    a = (d["u"], d["delta"], d["A"], d["B"], d["C"])
+    out = scan_fwd(*a, None, d["delta_bias"], True)[0]
+    out2 = scan_fwd(*a, None, d["delta_bias"], True)[0]
+    assert torch.equal(out, out2)
+    sl = scan_fwd(d["u"][3:5], d["delta"][3:5], d["A"], d["B"][3:5], d["C"][3:5], None, d["delta_bias"], True)[0]
+    assert torch.equal(sl, out[3:5])
+    lin = scan_fwd(2.5 * d["u"], d["delta"], d["A"], d["B"], d["C"], None, d["delta_bias"], True)[0]
+    assert rel_err(lin, 2.5 * out) < 1e-5
+    per = dim // G
+    grp = scan_fwd(d["u"][:, per:2 * per], d["delta"][:, per:2 * per], d["A"][per:2 * per], d["B"][:, 1:2], d["C"][:, 1:2],
+                   None, d["delta_bias"][per:2 * per], True)[0]
+    assert torch.equal(grp, out[:, per:2 * per])
+    assert torch.isfinite(out).all()
