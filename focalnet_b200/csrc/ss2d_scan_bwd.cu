@@ -123,11 +123,7 @@ __device__ __forceinline__ void bwd_state(uint32_t bc, uint32_t wa, int nsb_rt, 
 #undef SS2D_ACC
         static_assert(NW <= 16, "reduction unrolled for at most 16 warps");
         if (red_vec && red_valid >= 4) {
-#ifdef SS2D_BWD_KNOCK_ST
-            *reinterpret_cast<float4 *>(red_dst) = acc;
-#else
             red_add_v4(red_dst, acc.x, acc.y, acc.z, acc.w);
-#endif
         } else {
             if (red_valid > 0) atomicAdd(red_dst + 0, acc.x);
             if (red_valid > 1) atomicAdd(red_dst + 1, acc.y);

@@ -162,11 +162,13 @@ def scan_bwd(u, delta, A, B, C, D, delta_bias, dout, x=None, delta_softplus=Fals
     if ckpt is None and L > _lib.CKPT_STEPS:
         scratch = torch.empty((batch, dim, _n_fine(L), N), device=u.device, dtype=torch.float32)
     du, ddelta = torch.empty_like(u, memory_format=torch.contiguous_format), torch.empty_like(delta, memory_format=torch.contiguous_format)
-    dA = torch.zeros_like(A)
-    dB = torch.zeros((batch, G, N, L), device=u.device, dtype=torch.float32)
-    dC = torch.zeros_like(dB)
-    dD = torch.zeros_like(D) if D is not None else None
-    dbias = torch.zeros_like(delta_bias) if delta_bias is not None else None
+    # the accumulated gradients share ONE zero-filled fp32 buffer (one memset instead of five)
+    n_bc, n_a = batch * G * N * L, dim * N
+    acc = torch.zeros(2 * n_bc + n_a + 2 * dim, device=u.device, dtype=torch.float32)
+    dB, dC = acc[:n_bc].view(batch, G, N, L), acc[n_bc:2 * n_bc].view(batch, G, N, L)
+    dA = acc[2 * n_bc:2 * n_bc + n_a].view(dim, N)
+    dD = acc[2 * n_bc + n_a:2 * n_bc + n_a + dim] if D is not None else None
+    dbias = acc[2 * n_bc + n_a + dim:] if delta_bias is not None else None
     dz = torch.empty_like(u, memory_format=torch.contiguous_format) if z is not None else None
     P = _lib.ScanBwdParams()
     _fill_fwd(P.f, u, delta, A, B, C, D, delta_bias, z, delta_softplus, dout.dtype, dims)
