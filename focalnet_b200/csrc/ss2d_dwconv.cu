@@ -36,17 +36,24 @@ __device__ __forceinline__ void dw_stage(float (*tile)[kPw + 2][kCw], const floa
                                          const DwGeom &g, int b, int h, int w0, int c0) {
     const int tx = threadIdx.x, ty = threadIdx.y;
     const int c = c0 + tx;
+    constexpr int kIt = (kPw + 2 + kTy - 1) / kTy;
+    float v[3][kIt];
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
         const int hh = h - 1 + r;
-        for (int wi = ty; wi < kPw + 2; wi += kTy) {
-            const int ww = w0 - 1 + wi;
-            float v = 0.f;
-            if (hh >= 0 && hh < g.H && ww >= 0 && ww < g.W && c < g.C)
-                v = __ldg(src + (((int64_t)b * g.H + hh) * g.W + ww) * cstride + c);
-            tile[r][wi][tx] = v;
+#pragma unroll
+        for (int k = 0; k < kIt; ++k) {
+            const int wi = ty + k * kTy, ww = w0 - 1 + wi;
+            v[r][k] = 0.f;
+            if (wi < kPw + 2 && hh >= 0 && hh < g.H && ww >= 0 && ww < g.W && c < g.C)
+                v[r][k] = __ldg(src + (((int64_t)b * g.H + hh) * g.W + ww) * cstride + c);
         }
     }
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int k = 0; k < kIt; ++k)
+            if (ty + k * kTy < kPw + 2) tile[r][ty + k * kTy][tx] = v[r][k];
 }
 
 // Forward: one block = 32 channels x 32 pixels x kTh rows.  The kTh+2 input rows are staged once (row re-read
@@ -69,16 +76,25 @@ __global__ void __launch_bounds__(kCw *kTy) dwconv_silu_fwd_kernel(const float *
 #pragma unroll
     for (int q = 0; q < 9; ++q) wgt[q] = c < g.C ? weight[c * 9 + q] : 0.f;
     const float bv = (bias && c < g.C) ? bias[c] : 0.f;
+    {   // all (kTh+2) x 5 loads of a thread are issued before the first use (memory-level parallelism)
+        constexpr int kIt = (kPw + 2 + kTy - 1) / kTy;
+        float v[kTh + 2][kIt];
 #pragma unroll
-    for (int r = 0; r < kTh + 2; ++r) {
-        const int hh = h0 - 1 + r;
-        for (int wi = ty; wi < kPw + 2; wi += kTy) {
-            const int ww = w0 - 1 + wi;
-            float v = 0.f;
-            if (hh >= 0 && hh < g.H && ww >= 0 && ww < g.W && c < g.C)
-                v = __ldg(xin + (((int64_t)b * g.H + hh) * g.W + ww) * g.cstride + c);
-            tin[r][wi][tx] = v;
+        for (int r = 0; r < kTh + 2; ++r) {
+            const int hh = h0 - 1 + r;
+#pragma unroll
+            for (int k = 0; k < kIt; ++k) {
+                const int wi = ty + k * kTy, ww = w0 - 1 + wi;
+                v[r][k] = 0.f;
+                if (wi < kPw + 2 && hh >= 0 && hh < g.H && ww >= 0 && ww < g.W && c < g.C)
+                    v[r][k] = __ldg(xin + (((int64_t)b * g.H + hh) * g.W + ww) * g.cstride + c);
+            }
         }
+#pragma unroll
+        for (int r = 0; r < kTh + 2; ++r)
+#pragma unroll
+            for (int k = 0; k < kIt; ++k)
+                if (ty + k * kTy < kPw + 2) tin[r][ty + k * kTy][tx] = v[r][k];
     }
     __syncthreads();
 #pragma unroll
@@ -138,7 +154,11 @@ __global__ void __launch_bounds__(kCw *kTy) dwconv_silu_dpre_kernel(const float 
     }
 }
 
-// pass 2: dxin = corr(dpre, flipped taps); dweight[c][tap] += sum dpre * xin(shifted); dbias[c] += sum dpre
+// pass 2: dxin = corr(dpre, flipped taps); dweight[c][tap] += sum dpre * xin(shifted); dbias[c] += sum dpre.
+// One block walks kGradRows rows x all W tiles of its 32-channel slab, so the dweight / dbias partial sums stay in
+// registers across ~32 tiles and only one atomicAdd per (channel, tap) per block reaches L2 (the first version
+// issued one per tile: 31 M atomics onto 1920 addresses at the training shape).
+constexpr int kGradRows = 8;
 __global__ void __launch_bounds__(kCw *kTy) dwconv_silu_grad_kernel(const float *__restrict__ xin, const float *__restrict__ weight,
                                                                    const float *__restrict__ dpre, float *__restrict__ dxin,
                                                                    int64_t dx_cstride, float *__restrict__ dweight,
@@ -146,34 +166,44 @@ __global__ void __launch_bounds__(kCw *kTy) dwconv_silu_grad_kernel(const float 
     __shared__ float tin[3][kPw + 2][kCw];
     __shared__ float tdp[3][kPw + 2][kCw];
     __shared__ float red[kTy][10][kCw];
-    int b, h, w0, c0;
-    dw_decode(g, b, h, w0, c0);
+    int id = blockIdx.x;
+    const int c0 = (id % g.tiles_c) * kCw; id /= g.tiles_c;
+    const int hblocks = (g.H + kGradRows - 1) / kGradRows;
+    const int hb = id % hblocks, b = id / hblocks;
     const int tx = threadIdx.x, ty = threadIdx.y;
     const int c = c0 + tx;
     float wgt[9];
 #pragma unroll
     for (int q = 0; q < 9; ++q) wgt[q] = c < g.C ? weight[c * 9 + q] : 0.f;
-    dw_stage(tin, xin, g.cstride, g, b, h, w0, c0);
-    dw_stage(tdp, dpre, g.C, g, b, h, w0, c0);
-    __syncthreads();
     float acc[10];
 #pragma unroll
     for (int q = 0; q < 10; ++q) acc[q] = 0.f;
-    for (int wi = ty; wi < kPw; wi += kTy) {
-        const int w = w0 + wi;
-        // input pixel (h, w) was read by output pixel (h+1-r, w+1-j) through tap (r, j)
-        float s = 0.f;
+    const int h_end = min(g.H, (hb + 1) * kGradRows);
+    for (int h = hb * kGradRows; h < h_end; ++h) {
+        for (int wt = 0; wt < g.tiles_w; ++wt) {
+            const int w0 = wt * kPw;
+            __syncthreads();  // previous tile fully consumed
+            dw_stage(tin, xin, g.cstride, g, b, h, w0, c0);
+            dw_stage(tdp, dpre, g.C, g, b, h, w0, c0);
+            __syncthreads();
 #pragma unroll
-        for (int r = 0; r < 3; ++r)
+            for (int k = 0; k < kPw / kTy; ++k) {
+                const int wi = ty + k * kTy, w = w0 + wi;
+                // input pixel (h, w) was read by output pixel (h+1-r, w+1-j) through tap (r, j)
+                float s = 0.f;
 #pragma unroll
-            for (int j = 0; j < 3; ++j) s = fmaf(wgt[r * 3 + j], tdp[2 - r][wi + 2 - j][tx], s);
-        if (c < g.C && w < g.W) dxin[(((int64_t)b * g.H + h) * g.W + w) * dx_cstride + c] = s;
-        const float gp = tdp[1][wi + 1][tx];  // dpre at output pixel (h, w); zero outside the image
+                for (int r = 0; r < 3; ++r)
 #pragma unroll
-        for (int r = 0; r < 3; ++r)
+                    for (int j = 0; j < 3; ++j) s = fmaf(wgt[r * 3 + j], tdp[2 - r][wi + 2 - j][tx], s);
+                if (c < g.C && w < g.W) dxin[(((int64_t)b * g.H + h) * g.W + w) * dx_cstride + c] = s;
+                const float gp = tdp[1][wi + 1][tx];  // dpre at output pixel (h, w); zero outside the image
 #pragma unroll
-            for (int j = 0; j < 3; ++j) acc[r * 3 + j] = fmaf(gp, tin[r][wi + j][tx], acc[r * 3 + j]);
-        acc[9] += gp;
+                for (int r = 0; r < 3; ++r)
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) acc[r * 3 + j] = fmaf(gp, tin[r][wi + j][tx], acc[r * 3 + j]);
+                acc[9] += gp;
+            }
+        }
     }
 #pragma unroll
     for (int q = 0; q < 10; ++q) red[ty][q][tx] = acc[q];
@@ -220,6 +250,7 @@ extern "C" int ss2d_dwconv_silu_bwd(const float *xin, int64_t cstride, const flo
     const unsigned grid = (unsigned)((int64_t)g.tiles_w * g.tiles_c * H * batch);
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     dwconv_silu_dpre_kernel<<<grid, dim3(kCw, kTy), 0, s>>>(xin, weight, bias, dout, dpre_scratch, g);
-    dwconv_silu_grad_kernel<<<grid, dim3(kCw, kTy), 0, s>>>(xin, weight, dpre_scratch, dxin, dx_cstride, dweight, dbias, g);
+    const unsigned grid2 = (unsigned)((int64_t)g.tiles_c * ((H + kGradRows - 1) / kGradRows) * batch);
+    dwconv_silu_grad_kernel<<<grid2, dim3(kCw, kTy), 0, s>>>(xin, weight, dpre_scratch, dxin, dx_cstride, dweight, dbias, g);
     return (int)cudaGetLastError();
 }
