@@ -311,8 +311,12 @@ def main():
                 ref = load_ref_cuda()
                 if ref is not None:
                     ro, rx = ref.fwd(*fargs, True, 1, True)
-                    rf, _ = kernel_ms(lambda: ref.fwd(*fargs, True, 1, True), 5)
-                    rb, _ = kernel_ms(lambda: ref.bwd(*fargs, d["dout"], rx, True, 1), 5)
+                    for _ in range(3):  # warm-up (module load, allocator) before timing the comparison arm
+                        ref.fwd(*fargs, True, 1, True)
+                        ref.bwd(*fargs, d["dout"], rx, True, 1)
+                    torch.cuda.synchronize()
+                    rf, _ = kernel_ms(lambda: ref.fwd(*fargs, True, 1, True), 10)
+                    rb, _ = kernel_ms(lambda: ref.bwd(*fargs, d["dout"], rx, True, 1), 10)
                     line["ref_cuda_sm100a_rebuild"] = {"fwd_ms": rf, "bwd_ms": rb, "GBps": (fb + bb) / (rf + rb) / 1e6,
                                                        "note": "reference oflex kernels recompiled for sm_100a (oracle/_ref), same tensors"}
             except Exception as exc:  # comparison leg only
