@@ -127,8 +127,8 @@ def cpu_baseline(dtype_name, sample_batch=SAMPLE["batch"], sample_dim=SAMPLE["di
     `sample_batch` of the 8 batch rows and `sample_dim` of the 768 channels (all 4 groups, full L = 4096; the
     reference's autograd backward is O(L^2) in memory traffic, so L is what makes it slow and is kept)."""
     from oracle.ss2d_oracle import selective_scan_ref_port
-    if threads:
-        torch.set_num_threads(threads)
+    # torchrun exports OMP_NUM_THREADS=1; the CPU arm is allowed all the host threads it can use
+    torch.set_num_threads(threads or os.cpu_count() or 1)
     d = make_inputs("cpu", torch.float32, 0, batch=sample_batch, dim=sample_dim)
     leaves = {k: d[k].clone().requires_grad_() for k in ("u", "delta", "A", "B", "C", "D", "delta_bias")}
     t0 = time.perf_counter()
