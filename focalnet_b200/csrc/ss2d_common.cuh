@@ -178,6 +178,15 @@ __device__ __forceinline__ void load_block_cross(const T_ *__restrict__ plane, f
 __device__ __forceinline__ void red_add_f32(float *addr, float v) {
     asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(v) : "memory");
 }
+__device__ __forceinline__ void red_add_v4_if(bool p, float *addr, float a, float b, float c, float d) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred q;\n\t"
+        "setp.ne.b32 q, %0, 0;\n\t"
+        "@q red.global.add.v4.f32 [%1], {%2, %3, %4, %5};\n\t"
+        "}" ::"r"((int)p), "l"(addr), "f"(a), "f"(b), "f"(c), "f"(d)
+        : "memory");
+}
 __device__ __forceinline__ void red_add_v4(float *addr, float a, float b, float c, float d) {
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
@@ -254,6 +263,17 @@ template <int OFF> __device__ __forceinline__ float lds_f32(uint32_t a) {
 }
 template <int OFF> __device__ __forceinline__ void sts_f32(uint32_t a, float v) {
     asm volatile("st.shared.f32 [%0+%1], %2;" ::"r"(a), "n"(OFF), "f"(v) : "memory");
+}
+// Predicated store: inline asm inside an `if` forces a real branch (BRA + BSSY/BSYNC reconvergence) around one
+// instruction; carrying the predicate into the asm keeps the state loop branch-free.
+template <int OFF> __device__ __forceinline__ void sts_f32_if(bool p, uint32_t a, float v) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred q;\n\t"
+        "setp.ne.b32 q, %0, 0;\n\t"
+        "@q st.shared.f32 [%1+%2], %3;\n\t"
+        "}" ::"r"((int)p), "r"(a), "n"(OFF), "f"(v)
+        : "memory");
 }
 template <int OFF> __device__ __forceinline__ uint4 lds_v4(uint32_t a) {
     uint4 q;

@@ -94,9 +94,9 @@ __device__ __forceinline__ void bwd_state(uint32_t bc, uint32_t wa, int nsb_rt, 
         w[i] = fmaf(An, pq, w[i]);
         dA_acc = fmaf(dl[i], pq, dA_acc);
     }
-    if (lane == 0) sts_f32<R * 4>(dx_addr, dx);  // dx at this chunk's first step -> carry for the left chunk
+    sts_f32_if<R * 4>(lane == 0, dx_addr, dx);  // dx at this chunk's first step -> carry for the left chunk
     dA_acc += __shfl_xor_sync(0xffffffffu, dA_acc, 1);  // lane pairs share one slot: 16 partials per (warp, state)
-    if ((lane & 1) == 0) sts_f32<R * 64>(da, lds_f32<R * 64>(da) + dA_acc);
+    sts_f32_if<R * 64>((lane & 1) == 0, da, lds_f32<R * 64>(da) + dA_acc);
     // ---- dB/dC: reduce over the CTA's channels in shared memory, then one vector reduction per 4 steps ----
     if (!active) {
 #pragma unroll
@@ -122,9 +122,9 @@ __device__ __forceinline__ void bwd_state(uint32_t bc, uint32_t wa, int nsb_rt, 
         SS2D_ACC(8) SS2D_ACC(9) SS2D_ACC(10) SS2D_ACC(11) SS2D_ACC(12) SS2D_ACC(13) SS2D_ACC(14) SS2D_ACC(15)
 #undef SS2D_ACC
         static_assert(NW <= 16, "reduction unrolled for at most 16 warps");
-        if (red_vec && red_valid >= 4) {
-            red_add_v4(red_dst, acc.x, acc.y, acc.z, acc.w);
-        } else {
+        const bool fast = red_vec && red_valid >= 4;
+        red_add_v4_if(fast, red_dst, acc.x, acc.y, acc.z, acc.w);
+        if (!fast) {  // ragged tail / unaligned rows only
             if (red_valid > 0) atomicAdd(red_dst + 0, acc.x);
             if (red_valid > 1) atomicAdd(red_dst + 1, acc.y);
             if (red_valid > 2) atomicAdd(red_dst + 2, acc.z);

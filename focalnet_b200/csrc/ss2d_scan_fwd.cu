@@ -56,11 +56,9 @@ __device__ __forceinline__ void fwd_state(uint32_t bc, uint32_t wa, int nsb_rt, 
 #pragma unroll
     for (int i = 0; i < T; ++i) { h = fmaf(a[i], hin, hl[i]); y[i] = fmaf(Cv[i], h, y[i]); }
     // lanes whose block ends on a checkpoint boundary publish h there (the last slot is the chunk carry)
-    if (pub) sts_f32<R * 4>(pub_addr, h);
-    if (lane == kWarp - 1) {
-        const uint32_t p_addr = wa + (NSB_CT > 0 ? NSB_CT : nsb_rt);
-        sts_f32<R * 4>(p_addr, lds_f32<R * 4>(p_addr) * P);
-    }
+    sts_f32_if<R * 4>(pub, pub_addr, h);
+    const uint32_t p_addr = wa + (NSB_CT > 0 ? NSB_CT : nsb_rt);
+    sts_f32_if<R * 4>(lane == kWarp - 1, p_addr, lds_f32<R * 4>(p_addr) * P);  // lane 31 holds the chunk's prod a
 }
 
 template <typename in_t, int T, int SLOTS, int SB, int NSB_CT, int R = 0>
