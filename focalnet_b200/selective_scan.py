@@ -20,7 +20,6 @@ import torch
 from . import _lib
 
 _DT = {torch.float32: _lib.F32, torch.float16: _lib.F16, torch.bfloat16: _lib.BF16}
-_MAGIC = 0x55D2B200  # tags a checkpoint buffer allocated by scan_fwd (see _ckpt_of)
 
 
 def _chk(cond: bool, msg: str):
@@ -91,15 +90,14 @@ def _n_fine(L):
 
 
 def _alloc_x_ckpt(u, batch, dim, L, N):
-    """One fp32 buffer = [ x (batch,dim,n_ref,2N) | ckpt (batch,dim,n_fine,N) | magic ].
+    """One fp32 buffer = [ x (batch,dim,n_ref,2N) | ckpt (batch,dim,n_fine,N) | 1 pad word ].
 
     ``x`` is the contiguous leading view, so callers that only know the reference contract
     (``last_state = x[:, :, -1, 1::2]``, test_selective_scan.py:79) see exactly the reference tensor, while
     ``scan_bwd`` can find the fine checkpoints behind it (``_ckpt_of``) even when ``x`` travelled through the
     reference's own autograd Function (ITS/models/vmamba_layers.py:184,190)."""
     nx, nc = batch * dim * _n_ref(L) * 2 * N, batch * dim * _n_fine(L) * N
-    buf = torch.empty(nx + nc + 1, device=u.device, dtype=torch.float32)
-    buf[-1:].view(torch.int32).fill_(_MAGIC)
+    buf = torch.empty(nx + nc + 1, device=u.device, dtype=torch.float32)  # odd size = the signature _ckpt_of checks
     x = buf[:nx].view(batch, dim, _n_ref(L), 2 * N)
     ckpt = buf[nx:nx + nc].view(batch, dim, _n_fine(L), N)
     return x, ckpt
