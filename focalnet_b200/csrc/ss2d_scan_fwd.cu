@@ -140,16 +140,10 @@ scan_fwd_kernel(const ss2d_scan_fwd_params p, const int tiles_per_group, const F
         const int64_t t0 = (int64_t)ci * chunk;
         cp_async_wait<0>();
         __syncthreads();  // tile q visible to everyone; everyone is done with the buffer tile q+1 will overwrite
-        if (q + 1 < Q) {
-            const int sb1 = sb + 1 == n_sb ? 0 : sb + 1, ci1 = sb + 1 == n_sb ? ci + 1 : ci;
-            stage_bc<in_t, T, SB, NT>(tiles + ((q + 1) & 1) * FT::tile_bytes, Bg, Cg, p.B_nstride, p.C_nstride,
-                                      sb1 * SB, N, (int64_t)ci1 * chunk, L, fl.vec_bc);
-            cp_async_commit();
-        }
         const int64_t tl = t0 + lane * T;                 // first timestep of this lane's block
         const int valid = (int)min((int64_t)T, L - tl);   // may be <= 0
-        if (sb == 0) {
-            float uv[T];
+        float uv[T];
+        if (sb == 0) {  // this chunk's u / delta loads are issued first, ahead of the cp.async burst of the next tile
             if constexpr (CROSS) load_block_cross<in_t, T>(u_row, uv, g, tl, L, xinfo, fl.vec_u);
             else load_block<in_t, T>(u_row + tl, uv, valid, fl.vec_u);
             load_block<in_t, T>(d_row + tl, dl, valid, fl.vec_delta);
@@ -157,6 +151,14 @@ scan_fwd_kernel(const ss2d_scan_fwd_params p, const int tiles_per_group, const F
                 if constexpr (!CROSS) prefetch_l2(u_row + tl + chunk);
                 prefetch_l2(d_row + tl + chunk);
             }
+        }
+        if (q + 1 < Q) {
+            const int sb1 = sb + 1 == n_sb ? 0 : sb + 1, ci1 = sb + 1 == n_sb ? ci + 1 : ci;
+            stage_bc<in_t, T, SB, NT>(tiles + ((q + 1) & 1) * FT::tile_bytes, Bg, Cg, p.B_nstride, p.C_nstride,
+                                      sb1 * SB, N, (int64_t)ci1 * chunk, L, fl.vec_bc);
+            cp_async_commit();
+        }
+        if (sb == 0) {
 #pragma unroll
             for (int i = 0; i < T; ++i) {
                 float d = dl[i] + bias;
