@@ -243,15 +243,9 @@ scan_bwd_kernel(const ss2d_scan_bwd_params pb, const int tiles_per_group, const 
         const int64_t t0 = (int64_t)ci * chunk;
         cp_async_wait<0>();
         __syncthreads();
-        if (q + 1 < Q) {
-            const int sb1 = sb + 1 == n_sb ? 0 : sb + 1, ci1 = sb + 1 == n_sb ? ci - 1 : ci;
-            stage_bc<in_t, T, SB, NT>(tiles + ((q + 1) & 1) * FT::tile_bytes, Bg, Cg, p.B_nstride, p.C_nstride,
-                                      sb1 * SB, N, (int64_t)ci1 * chunk, L, fl.vec_bc);
-            cp_async_commit();
-        }
         const int64_t tl = t0 + lane * T;
         const int valid = (int)min((int64_t)T, L - tl);
-        if (sb == 0) {
+        if (sb == 0) {  // this chunk's global loads are issued first, ahead of the cp.async burst of the next tile
             if constexpr (CROSS) {
                 load_block_cross<in_t, T>(u_row, uv, g, tl, L, xinfo, fl.vec_u);
                 load_block_cross<out_t, T>(g_row, go, g, tl, L, xinfo, fl.vec_dout);
@@ -260,6 +254,18 @@ scan_bwd_kernel(const ss2d_scan_bwd_params pb, const int tiles_per_group, const 
                 load_block<out_t, T>(g_row + tl, go, valid, fl.vec_dout);
             }
             load_block<in_t, T>(d_row + tl, dl, valid, fl.vec_delta);
+            if (ci > 0) {  // pull the next (left) chunk's lines into L2 while this chunk computes
+                prefetch_l2(d_row + tl - chunk);
+                if constexpr (!CROSS) { prefetch_l2(u_row + tl - chunk); prefetch_l2(g_row + tl - chunk); }
+            }
+        }
+        if (q + 1 < Q) {
+            const int sb1 = sb + 1 == n_sb ? 0 : sb + 1, ci1 = sb + 1 == n_sb ? ci - 1 : ci;
+            stage_bc<in_t, T, SB, NT>(tiles + ((q + 1) & 1) * FT::tile_bytes, Bg, Cg, p.B_nstride, p.C_nstride,
+                                      sb1 * SB, N, (int64_t)ci1 * chunk, L, fl.vec_bc);
+            cp_async_commit();
+        }
+        if (sb == 0) {
             if (z_row) {  // out = pre * silu(z): dz and the gated upstream gradient
                 float zv[T], pre[T];
                 load_block<in_t, T>(z_row + tl, zv, valid, fl.vec_z);
