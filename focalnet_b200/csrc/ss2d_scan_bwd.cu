@@ -239,6 +239,7 @@ scan_bwd_kernel(const ss2d_scan_bwd_params pb, const int tiles_per_group, const 
     float dD_acc = 0.f, dbias_acc = 0.f;
 
     int ci = n_chunks - 1, sb = 0;
+    float hin_next = (ci > 0 && ck_row && lane < N && N <= kWarp) ? ck_row[((int64_t)ci * ckpt_per_chunk - 1) * N + lane] : 0.f;
     for (int q = 0; q < Q; ++q) {
         const int64_t t0 = (int64_t)ci * chunk;
         cp_async_wait<0>();
@@ -295,10 +296,16 @@ scan_bwd_kernel(const ss2d_scan_bwd_params pb, const int tiles_per_group, const 
             dlnext = __shfl_down_sync(0xffffffffu, dl[0], 1);
             if (lane == 31) dlnext = dl_first_right;
             qsum = dsum - dl[0] + dlnext;
-            // h entering this chunk, from the forward's fine checkpoints
+            // h entering this chunk, from the forward's fine checkpoints; the value for the NEXT (left) chunk is
+            // fetched now into a register so that its global-load latency hides behind this chunk's 16 states
             __syncwarp();
-            for (int n = lane; n < N; n += kWarp)
-                sHin[n] = (ci > 0 && ck_row) ? ck_row[((int64_t)ci * ckpt_per_chunk - 1) * N + n] : 0.f;
+            if (N <= kWarp) {
+                if (lane < N) sHin[lane] = hin_next;
+                hin_next = (ci > 1 && ck_row && lane < N) ? ck_row[((int64_t)(ci - 1) * ckpt_per_chunk - 1) * N + lane] : 0.f;
+            } else {
+                for (int n = lane; n < N; n += kWarp)
+                    sHin[n] = (ci > 0 && ck_row) ? ck_row[((int64_t)ci * ckpt_per_chunk - 1) * N + n] : 0.f;
+            }
             __syncwarp();
         }
         {
