@@ -188,6 +188,56 @@ class FusedCrossScanFn(torch.autograd.Function):
         return dx.view(B, D, H, W).to(x.dtype), ddelta, dA, dB.to(Bs.dtype), dC.to(Cs.dtype), dDs, dbias, None
 
 
+class MergeNormGateFn(torch.autograd.Function):
+    """y (B,D,L) fp32 spatial  ->  LayerNorm_D(y^T) [* silu(z)]  as (B,L,D) channels-last, one kernel
+    (ss2d_merge_norm_gate_fwd/_bwd).  `z` is a channels-last view whose last dim has stride 1 (e.g. the z-half
+    ``xz[..., D:]`` of the in_proj output); its pixel stride is passed through, no copy is made."""
+
+    @staticmethod
+    def forward(ctx, y, weight, bias, eps, z):
+        B, D, L = y.shape
+        _chk(y.is_cuda and y.dtype == torch.float32, "merge_norm_gate: y must be a float32 CUDA tensor (no CPU path)")
+        y = y.contiguous()
+        w, bb = weight.contiguous().float(), bias.contiguous().float()
+        zs, zshape = 0, None
+        if z is not None:
+            zshape = tuple(z.shape)
+            _chk(z.dtype == torch.float32 and z.is_cuda and z.shape[-1] == D and z.numel() == B * L * D and z.stride(-1) == 1,
+                 "merge_norm_gate: z must be float32 channels-last with D channels per pixel")
+            zz = z.reshape(B * L, D) if z.dim() != 2 else z
+            if zz.stride(1) != 1 or (B * L > 1 and zz.stride(0) < D):
+                zz = zz.contiguous()
+            z, zs = zz, zz.stride(0) if B * L > 1 else D
+        out = torch.empty((B, L, D), device=y.device, dtype=torch.float32)
+        with torch.cuda.device(y.device):
+            _lib.check(_lib.lib().ss2d_merge_norm_gate_fwd(y.data_ptr(), w.data_ptr(), bb.data_ptr(), float(eps), _ptr(z), zs,
+                                                          out.data_ptr(), B, D, L, _stream(y)), "ss2d_merge_norm_gate_fwd")
+        ctx.save_for_backward(y, w, bb, z)
+        ctx.eps, ctx.zs, ctx.zshape = float(eps), zs, zshape
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        y, w, bb, z = ctx.saved_tensors
+        B, D, L = y.shape
+        dout = dout.contiguous().float()
+        dy = torch.empty_like(y)
+        dwb = torch.zeros(2 * D, device=y.device, dtype=torch.float32)
+        dz = torch.empty((B * L, D), device=y.device, dtype=torch.float32) if z is not None else None
+        with torch.cuda.device(y.device):
+            _lib.check(_lib.lib().ss2d_merge_norm_gate_bwd(y.data_ptr(), w.data_ptr(), bb.data_ptr(), ctx.eps, _ptr(z), ctx.zs,
+                                                          dout.data_ptr(), dy.data_ptr(), _ptr(dz), D, dwb.data_ptr(),
+                                                          dwb[D:].data_ptr(), B, D, L, _stream(y)), "ss2d_merge_norm_gate_bwd")
+        return dy, dwb[:D], dwb[D:], None, (dz.view(ctx.zshape) if dz is not None else None)
+
+
+def merge_norm_gate(y, weight, bias, eps=1e-5, z=None):
+    """LayerNorm over channels of the merged scan output y (B,D,L), transposed to (B,L,D), optionally * silu(z)."""
+    B, D, L = y.shape
+    out = MergeNormGateFn.apply(y, weight, bias, eps, z)
+    return out
+
+
 def _to_scan_order(t: torch.Tensor, H: int, W: int) -> torch.Tensor:
     """t (B,4,C,L) holding direction k's rows in SPATIAL order -> each direction's own scan order.  Only ever
     applied to the small x_dbl (R+2N = 38 rows per direction), never to x (d_inner = 192 rows)."""
@@ -247,9 +297,33 @@ def cross_selective_scan(
                                delta_softplus)
     if out_norm_shape in ["v1"]:
         y = out_norm(y.view(B, -1, H, W)).permute(0, 2, 3, 1)
+    elif isinstance(out_norm, torch.nn.LayerNorm) and out_norm.elementwise_affine and out_norm.bias is not None and \
+            tuple(out_norm.normalized_shape) == (D,) and D <= 512:
+        # transpose + LayerNorm in one kernel (row N1 of SURVEY §8f) instead of a transpose copy + ATen LayerNorm
+        y = merge_norm_gate(y, out_norm.weight, out_norm.bias, out_norm.eps).view(B, H, W, -1)
     else:
         y = out_norm(y.transpose(1, 2).contiguous()).view(B, H, W, -1)
     return y.to(x.dtype) if to_dtype else y
+
+
+def ss2d_forward(m: torch.nn.Module, x: torch.Tensor) -> torch.Tensor:
+    """SS2D.forwardv2 (vmamba_layers.py:583-601) on this library's kernels, for an *unchanged* reference SS2D module `m`
+    (fp32, d_conv == 3, LayerNorm out_norm, z gate with SiLU): in_proj -> dwconv3x3+SiLU pre-mix (no permute copy) ->
+    fused 4-direction scan -> transpose+LayerNorm+z-gate epilogue (one kernel) -> out_proj."""
+    xz = m.in_proj(x)                                        # (B, H, W, 2*d_inner)
+    B, H, W, _ = xz.shape
+    D = m.conv2d.out_channels
+    xc = dwconv_silu(xz.contiguous(), m.conv2d.weight, m.conv2d.bias, D)
+    N = m.A_logs.shape[1]
+    K, _, R = m.dt_projs_weight.shape
+    L = H * W
+    x_dbl = torch.matmul(m.x_proj_weight.reshape(K * (R + 2 * N), D), xc.reshape(B, D, L))
+    x_dbl = _to_scan_order(x_dbl.view(B, K, R + 2 * N, L), H, W)
+    dts_lr, Bs, Cs = torch.split(x_dbl, [R, N, N], dim=2)
+    dts = torch.matmul(m.dt_projs_weight.unsqueeze(0), dts_lr).reshape(B, K * D, L)
+    y = FusedCrossScanFn.apply(xc, dts, -torch.exp(m.A_logs.float()), Bs, Cs, m.Ds.float(), m.dt_projs_bias.reshape(-1).float(), True)
+    y = merge_norm_gate(y, m.out_norm.weight, m.out_norm.bias, m.out_norm.eps, z=xz[..., D:]).view(B, H, W, D)
+    return m.dropout(m.out_proj(y))
 
 
 def patch_ss2d(model: torch.nn.Module) -> int:

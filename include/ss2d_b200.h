@@ -17,6 +17,7 @@
  *   ss2d_cross_scan_fwd/_bwd  (fused) CrossScan -> selective scan -> CrossMerge, i.e. the body of
  *                             cross_selective_scan  ITS/models/vmamba_layers.py:261-291 without the 4x copies
  *   ss2d_dwconv_silu_fwd/_bwd permute + depthwise 3x3 conv + bias + SiLU  ITS/models/vmamba_layers.py:460-469,591-594
+ *   ss2d_merge_norm_gate_fwd/_bwd  transpose + LayerNorm (+ z gate)       ITS/models/vmamba_layers.py:296-297,599
  *
  * Struct fields mirror SSMParamsBase / SSMParamsBwd (csrc/selective_scan/selective_scan.h:26-90) with
  * 64-bit strides (the reference's uint32 strides overflow past 4.29 G elements).  Strides are in ELEMENTS.
@@ -163,6 +164,22 @@ int ss2d_dwconv_silu_fwd(const float *xin, int64_t cstride, const float *weight,
 int ss2d_dwconv_silu_bwd(const float *xin, int64_t cstride, const float *weight, const float *bias, const float *dout,
                          float *dpre_scratch, float *dxin, int64_t dx_cstride, float *dweight, float *dbias,
                          int64_t batch, int64_t C, int64_t H, int64_t W, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * epilogue of the SS2D core: transpose + LayerNorm over the D channels (+ SiLU gate) in one pass.
+ *   y    : (batch, D, L) f32, the merged scan output in spatial order (ss2d_cross_fwd_params.y)
+ *   weight, bias : (D) f32 LayerNorm affine ; eps as nn.LayerNorm
+ *   z    : NULL, or the raw z-half of the in_proj output, channels-last: pixel (b,l) starts at z + (b*L+l)*z_pstride
+ *          (vmamba_layers.py:587-589,599: z = act(z); y = y * z) ; out : (batch, L, D) f32 channels-last
+ * replaces y.transpose(1,2).contiguous() + out_norm(y) (+ y * z)  ITS/models/vmamba_layers.py:296-297,599.  D <= 512.
+ * bwd: dout (batch,L,D) -> dy (batch,D,L); dz (first D channels of every pixel, dz_pstride) or NULL;
+ *      dweight, dbias (D) f32 ZEROED (accumulated).
+ * ------------------------------------------------------------------------------------------- */
+int ss2d_merge_norm_gate_fwd(const float *y, const float *weight, const float *bias, float eps, const float *z,
+                             int64_t z_pstride, float *out, int64_t batch, int64_t D, int64_t L, void *stream);
+int ss2d_merge_norm_gate_bwd(const float *y, const float *weight, const float *bias, float eps, const float *z,
+                             int64_t z_pstride, const float *dout, float *dy, float *dz, int64_t dz_pstride,
+                             float *dweight, float *dbias, int64_t batch, int64_t D, int64_t L, void *stream);
 
 #ifdef __cplusplus
 }

@@ -203,3 +203,77 @@ def test_full_ss2d_block_matches_torch_composition():
     assert rel_err(o1, o2) < 1e-3
     for k in p:
         assert rel_err(q1[k].grad, q2[k].grad) < 2e-3, k
+
+
+@pytest.mark.parametrize("shape", [(2, 192, 64 * 64), (1, 48, 37), (3, 200, 130), (1, 512, 64)])
+@pytest.mark.parametrize("gate", [False, True])
+def test_merge_norm_gate_matches_torch(shape, gate):
+    """transpose + LayerNorm (+ z gate) epilogue (vmamba_layers.py:296-297,599) against the library ops in fp64."""
+    from focalnet_b200 import merge_norm_gate
+    B, D, L = shape
+    g = torch.Generator().manual_seed(D + L)
+    y = torch.randn(B, D, L, generator=g).cuda().requires_grad_()
+    w = (1 + 0.2 * torch.randn(D, generator=g)).cuda().requires_grad_()
+    b = (0.2 * torch.randn(D, generator=g)).cuda().requires_grad_()
+    xz = torch.randn(B, L, 2 * D, generator=g).cuda().requires_grad_()
+    go = torch.randn(B, L, D, generator=g).cuda()
+    out = merge_norm_gate(y, w, b, 1e-5, z=xz[..., D:] if gate else None)
+    out.backward(go)
+    yr, wr, br, xr = (t.detach().double().requires_grad_() for t in (y, w, b, xz))
+    ref = torch.nn.functional.layer_norm(yr.transpose(1, 2), (D,), wr, br, 1e-5)
+    if gate:
+        ref = ref * torch.nn.functional.silu(xr[..., D:])
+    ref.backward(go.double())
+    assert rel_err(out, ref) < 1e-5
+    assert rel_err(y.grad, yr.grad) < 1e-4 and rel_err(w.grad, wr.grad) < 1e-4 and rel_err(b.grad, br.grad) < 1e-4
+    if gate:
+        assert rel_err(xz.grad, xr.grad) < 1e-4
+
+
+def test_ss2d_forward_on_reference_shaped_module():
+    """ss2d_forward drives a module with the attribute layout of the reference's SS2D (in_proj, conv2d, x_proj_weight,
+    dt_projs_weight/bias, A_logs, Ds, out_norm, out_proj, dropout) and must equal the torch composition."""
+    from focalnet_b200 import ss2d_forward
+    from oracle import ss2d_oracle as orc
+    torch.manual_seed(1)
+    dm, D, N, R, K = 16, 32, 16, 1, 4
+
+    class M(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.in_proj = torch.nn.Linear(dm, 2 * D, bias=False)
+            self.conv2d = torch.nn.Conv2d(D, D, 3, padding=1, groups=D)
+            self.x_proj_weight = torch.nn.Parameter(torch.randn(K, R + 2 * N, D) * D ** -0.5)
+            self.dt_projs_weight = torch.nn.Parameter((torch.rand(K, D, R) * 2 - 1))
+            self.dt_projs_bias = torch.nn.Parameter(torch.rand(K, D) * 2 - 4)
+            self.A_logs = torch.nn.Parameter(torch.log(torch.arange(1, N + 1.0)).repeat(K * D, 1))
+            self.Ds = torch.nn.Parameter(torch.ones(K * D))
+            self.out_norm = torch.nn.LayerNorm(D)
+            self.out_proj = torch.nn.Linear(D, dm, bias=False)
+            self.dropout = torch.nn.Identity()
+
+    m = M().cuda()
+    x = torch.randn(2, 9, 11, dm).cuda()
+    out = ss2d_forward(m, x)
+    out.sum().backward()
+    g1 = {k: v.grad.clone() for k, v in m.named_parameters()}
+    m.zero_grad()
+    md = M().cuda().double()
+    md.load_state_dict({k: v.double() for k, v in m.state_dict().items()})
+    xd = x.double()
+    xz = md.in_proj(xd)
+    B, H, W, _ = xz.shape
+    z = torch.nn.functional.silu(xz[..., D:])
+    xc = torch.nn.functional.silu(md.conv2d(xz[..., :D].permute(0, 3, 1, 2)))
+    xs = orc.cross_scan_port(xc)
+    x_dbl = torch.einsum("bkdl,kcd->bkcl", xs, md.x_proj_weight)
+    dts, Bs, Cs = torch.split(x_dbl, [R, N, N], dim=2)
+    dts = torch.einsum("bkrl,kdr->bkdl", dts, md.dt_projs_weight).reshape(B, K * D, H * W)
+    ys = orc.selective_scan_ref_port(xs.reshape(B, K * D, H * W), dts, -torch.exp(md.A_logs), Bs, Cs, md.Ds, None,
+                                     md.dt_projs_bias.reshape(-1), True, compute_dtype=torch.float64)
+    y = md.out_norm(orc.cross_merge_port(ys.view(B, K, D, H, W)).transpose(1, 2)).view(B, H, W, D)
+    ref = md.out_proj(y * z)
+    ref.sum().backward()
+    assert rel_err(out, ref) < 1e-3
+    for k, v in md.named_parameters():
+        assert rel_err(g1[k], v.grad) < 2e-3, k
