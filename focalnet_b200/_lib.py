@@ -53,7 +53,7 @@ class CrossBwdParams(C.Structure):
 EXPORTS = ("ss2d_abi_version", "ss2d_build_info", "ss2d_error_string", "ss2d_selective_scan_fwd",
            "ss2d_selective_scan_bwd", "ss2d_cross_scan", "ss2d_cross_merge", "ss2d_cross_scan_fwd",
            "ss2d_cross_scan_bwd", "ss2d_dwconv_silu_fwd", "ss2d_dwconv_silu_bwd", "ss2d_merge_norm_gate_fwd",
-           "ss2d_merge_norm_gate_bwd")
+           "ss2d_merge_norm_gate_bwd", "ss2d_cross_permute")
 
 _lib = None
 
@@ -76,6 +76,7 @@ def lib():
         sigs.update({n: [_vp, _vp, _i64, _i64, _i64, _i64, _i32, _vp] for n in ("ss2d_cross_scan", "ss2d_cross_merge")})
         sigs["ss2d_dwconv_silu_fwd"] = [_vp, _i64, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _vp]
         sigs["ss2d_dwconv_silu_bwd"] = [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _i64, _i64, _i64, _i64, _vp]
+        sigs["ss2d_cross_permute"] = [_vp, _vp, _i64, _i64, _i64, _i64, _i32, _i32, _vp]
         _f32 = C.c_float
         sigs["ss2d_merge_norm_gate_fwd"] = [_vp, _vp, _vp, _f32, _vp, _i64, _vp, _i64, _i64, _i64, _vp]
         sigs["ss2d_merge_norm_gate_bwd"] = [_vp, _vp, _vp, _f32, _vp, _i64, _vp, _vp, _vp, _i64, _vp, _vp, _i64, _i64, _i64, _vp]

@@ -101,6 +101,74 @@ __global__ void __launch_bounds__(kTile *kRows) cross_merge_kernel(const T *__re
     }
 }
 
+// Per-direction permutation ("1b1", cf. triton_cross_scan_1b1, csm_triton.py:83-120): plane (b,k,c) of src holds
+// direction k's rows in SPATIAL order and is rewritten in direction k's SCAN order (INVERSE: the other way round).
+// Used by the fused path on the small x_dbl tensor (R+2N = 38 rows per direction) and on its gradient.
+template <typename T, bool INVERSE>
+__global__ void __launch_bounds__(kTile *kRows) cross_permute_kernel(const T *__restrict__ src, T *__restrict__ dst, int C, int H,
+                                                                      int W) {
+    __shared__ T tile[kTile][kTile + 1];
+    const int64_t L = (int64_t)H * W;
+    const int tiles_w = (W + kTile - 1) / kTile, tiles_h = (H + kTile - 1) / kTile;
+    const int plane = blockIdx.x / (tiles_w * tiles_h), tile_id = blockIdx.x % (tiles_w * tiles_h);
+    const int k = (plane / C) % 4;
+    const int h0 = (tile_id / tiles_w) * kTile, w0 = (tile_id % tiles_w) * kTile;
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const T *s = src + (int64_t)plane * L;
+    T *d = dst + (int64_t)plane * L;
+    const bool flip = k >= 2;
+    if ((k & 1) == 0) {  // row-major both sides: straight or mirrored copy
+#pragma unroll
+        for (int r = 0; r < kTile; r += kRows) {
+            const int h = h0 + ty + r, w = w0 + tx;
+            if (h < H && w < W) {
+                const int64_t l = (int64_t)h * W + w, lp = flip ? L - 1 - l : l;
+                if (INVERSE) d[l] = s[lp]; else d[lp] = s[l];
+            }
+        }
+        return;
+    }
+    // column-major scan order on one side: turn the 32x32 tile through shared memory
+#pragma unroll
+    for (int r = 0; r < kTile; r += kRows) {
+        if (!INVERSE) {
+            const int h = h0 + ty + r, w = w0 + tx;
+            if (h < H && w < W) tile[ty + r][tx] = s[(int64_t)h * W + w];
+        } else {
+            const int w = w0 + ty + r, h = h0 + tx;
+            if (h < H && w < W) {
+                const int64_t l = (int64_t)w * H + h;
+                tile[tx][ty + r] = s[flip ? L - 1 - l : l];
+            }
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < kTile; r += kRows) {
+        if (!INVERSE) {
+            const int w = w0 + ty + r, h = h0 + tx;
+            if (h < H && w < W) {
+                const int64_t l = (int64_t)w * H + h;
+                d[flip ? L - 1 - l : l] = tile[tx][ty + r];
+            }
+        } else {
+            const int h = h0 + ty + r, w = w0 + tx;
+            if (h < H && w < W) d[(int64_t)h * W + w] = tile[ty + r][tx];
+        }
+    }
+}
+
+template <typename T>
+static int launch_permute(bool inverse, const void *in, void *out, int64_t B, int64_t C, int64_t H, int64_t W, cudaStream_t s) {
+    dim3 block(kTile, kRows);
+    dim3 grid((unsigned)(((W + kTile - 1) / kTile) * ((H + kTile - 1) / kTile) * B * 4 * C));
+    if (inverse)
+        cross_permute_kernel<T, true><<<grid, block, 0, s>>>(static_cast<const T *>(in), static_cast<T *>(out), (int)C, (int)H, (int)W);
+    else
+        cross_permute_kernel<T, false><<<grid, block, 0, s>>>(static_cast<const T *>(in), static_cast<T *>(out), (int)C, (int)H, (int)W);
+    return (int)cudaGetLastError();
+}
+
 template <typename T>
 static int launch_cross(bool merge, const void *in, void *out, int64_t B, int64_t C, int64_t H, int64_t W, cudaStream_t s) {
     dim3 block(kTile, kRows);
@@ -132,4 +200,18 @@ extern "C" int ss2d_cross_scan(const void *x, void *xs, int64_t B, int64_t C, in
 }
 extern "C" int ss2d_cross_merge(const void *ys, void *y, int64_t B, int64_t C, int64_t H, int64_t W, int32_t dtype, void *stream) {
     return ss2d::cross_dispatch(true, ys, y, B, C, H, W, dtype, stream);
+}
+
+extern "C" int ss2d_cross_permute(const void *src, void *dst, int64_t B, int64_t C, int64_t H, int64_t W, int32_t dtype,
+                                  int32_t inverse, void *stream) {
+    using namespace ss2d;
+    if (!src || !dst || B <= 0 || C <= 0 || H <= 0 || W <= 0) return SS2D_EINVAL;
+    if (((W + kTile - 1) / kTile) * ((H + kTile - 1) / kTile) * B * 4 * C > 0x7fffffffLL) return SS2D_EINVAL;
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    switch (dtype) {
+        case SS2D_F32: return launch_permute<float>(inverse != 0, src, dst, B, C, H, W, s);
+        case SS2D_F16: return launch_permute<__half>(inverse != 0, src, dst, B, C, H, W, s);
+        case SS2D_BF16: return launch_permute<__nv_bfloat16>(inverse != 0, src, dst, B, C, H, W, s);
+        default: return SS2D_EDTYPE;
+    }
 }

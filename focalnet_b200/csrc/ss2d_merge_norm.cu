@@ -217,7 +217,9 @@ extern "C" int ss2d_merge_norm_gate_bwd(const float *y, const float *weight, con
         return SS2D_EINVAL;
     if (z && (z_pstride < D || (dz && dz_pstride < D))) return SS2D_EINVAL;
     const int64_t tiles = (L + kMnPix - 1) / kMnPix;
-    const int tpb = 4;  // tiles per block: keeps the dweight / dbias atomics at one per channel per 128 pixels
+    // tiles per block: as many as keep >= ~4 blocks per SM (the dweight / dbias partial sums stay in registers across them)
+    int tpb = (int)(tiles * batch / 600);
+    tpb = tpb < 1 ? 1 : (tpb > 8 ? 8 : tpb);
     const int64_t blocks = (tiles * batch + tpb - 1) / tpb;
     if (blocks > 0x7fffffffLL) return SS2D_EINVAL;
     const size_t smem = mn_smem((int)D);

@@ -238,16 +238,35 @@ def merge_norm_gate(y, weight, bias, eps=1e-5, z=None):
     return out
 
 
+class ToScanOrderFn(torch.autograd.Function):
+    """t (B,4,C,L), plane k in SPATIAL order -> each direction's own scan order (ss2d_cross_permute); the backward is the
+    inverse permutation.  Only ever applied to the small x_dbl (R+2N = 38 rows per direction), never to x (192 rows)."""
+
+    @staticmethod
+    def forward(ctx, t, H, W):
+        B, K, Cn, L = t.shape
+        _chk(K == 4 and L == H * W and t.is_cuda and t.dtype in _DT, "to_scan_order: (B,4,C,H*W) CUDA tensor expected")
+        t = t.contiguous()
+        out = torch.empty_like(t)
+        ctx.dims = (B, Cn, H, W)
+        with torch.cuda.device(t.device):
+            _lib.check(_lib.lib().ss2d_cross_permute(t.data_ptr(), out.data_ptr(), B, Cn, H, W, _DT[t.dtype], 0, _stream(t)),
+                       "ss2d_cross_permute")
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        B, Cn, H, W = ctx.dims
+        g = g.contiguous()
+        out = torch.empty_like(g)
+        with torch.cuda.device(g.device):
+            _lib.check(_lib.lib().ss2d_cross_permute(g.data_ptr(), out.data_ptr(), B, Cn, H, W, _DT[g.dtype], 1, _stream(g)),
+                       "ss2d_cross_permute")
+        return out, None, None
+
+
 def _to_scan_order(t: torch.Tensor, H: int, W: int) -> torch.Tensor:
-    """t (B,4,C,L) holding direction k's rows in SPATIAL order -> each direction's own scan order.  Only ever
-    applied to the small x_dbl (R+2N = 38 rows per direction), never to x (d_inner = 192 rows)."""
-    B, K, Cn, L = t.shape
-    out = torch.empty_like(t)
-    out[:, 0] = t[:, 0]
-    out[:, 1] = t[:, 1].view(B, Cn, H, W).transpose(2, 3).reshape(B, Cn, L)
-    out[:, 2] = t[:, 2].flip(-1)
-    out[:, 3] = t[:, 3].view(B, Cn, H, W).transpose(2, 3).reshape(B, Cn, L).flip(-1)
-    return out
+    return ToScanOrderFn.apply(t, H, W)
 
 
 def cross_selective_scan(

@@ -110,6 +110,12 @@ int ss2d_cross_scan(const void *x, void *xs, int64_t B, int64_t C, int64_t H, in
 /* ys:(B,4,C,H*W) -> y:(B,C,H*W) (spatial order), sum of the four un-permuted directions */
 int ss2d_cross_merge(const void *ys, void *y, int64_t B, int64_t C, int64_t H, int64_t W, int32_t dtype, void *stream);
 
+/* src:(B,4,C,H*W), plane (b,k,c) in SPATIAL order -> dst: same planes, each in its direction k's SCAN order
+ * (inverse != 0: scan order -> spatial).  The per-direction ("1b1") permutation of triton_cross_scan_1b1
+ * (csm_triton.py:83-120); the fused path applies it to the 38-row x_dbl and to its gradient only. */
+int ss2d_cross_permute(const void *src, void *dst, int64_t B, int64_t C, int64_t H, int64_t W, int32_t dtype, int32_t inverse,
+                       void *stream);
+
 /* ---------------------------------------------------------------------------------------------
  * fused SS2D core (seam S3): CrossScan and CrossMerge are applied in the scan kernel's load / store
  * addressing — no (B,4,D,L) copy of x (100.7 MB at the microbench) and no (B,4,D,L) ys is ever materialised.

@@ -277,3 +277,19 @@ def test_ss2d_forward_on_reference_shaped_module():
     assert rel_err(out, ref) < 1e-3
     for k, v in md.named_parameters():
         assert rel_err(g1[k], v.grad) < 2e-3, k
+
+
+@pytest.mark.parametrize("shape", [(2, 38, 64, 64), (1, 5, 30, 41), (1, 3, 1, 9)])
+def test_cross_permute_is_per_direction_scan_order_and_invertible(shape):
+    from focalnet_b200.ss2d import ToScanOrderFn
+    from oracle import ss2d_oracle as orc
+    B, C, H, W = shape
+    t = torch.randn(B, 4, C, H * W).cuda().requires_grad_()
+    out = ToScanOrderFn.apply(t, H, W)
+    for k in range(4):   # direction k of the full cross-scan of plane-set k
+        ref = orc.cross_scan(t.detach()[:, k].reshape(B, C, H, W))[:, k]
+        assert torch.equal(out[:, k].cpu(), torch.from_numpy(ref))
+    g = torch.randn_like(out)
+    out.backward(g)
+    back = ToScanOrderFn.apply(t.grad, H, W)       # permuting the gradient again must give g back (inverse map)
+    assert torch.equal(back, g)
