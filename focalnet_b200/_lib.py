@@ -12,8 +12,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libss2d_b200.so")
 
 F32, F16, BF16 = 0, 1, 2
-CKPT_STEPS = 256
 REF_CHUNK = 2048
+SL_BLOCK = 16  # sequences up to this length need no checkpoints at all
 
 _vp, _i64, _i32 = C.c_void_p, C.c_int64, C.c_int32
 
@@ -50,7 +50,7 @@ class CrossBwdParams(C.Structure):
                                                              "dDskip", "ddelta_bias")]
 
 
-EXPORTS = ("ss2d_abi_version", "ss2d_build_info", "ss2d_error_string", "ss2d_selective_scan_fwd",
+EXPORTS = ("ss2d_abi_version", "ss2d_build_info", "ss2d_error_string", "ss2d_scan_ckpt_floats", "ss2d_selective_scan_fwd",
            "ss2d_selective_scan_bwd", "ss2d_cross_scan", "ss2d_cross_merge", "ss2d_cross_scan_fwd",
            "ss2d_cross_scan_bwd", "ss2d_dwconv_silu_fwd", "ss2d_dwconv_silu_bwd", "ss2d_merge_norm_gate_fwd",
            "ss2d_merge_norm_gate_bwd", "ss2d_cross_permute")
@@ -71,6 +71,8 @@ def lib():
         L.ss2d_build_info.restype = C.c_char_p
         L.ss2d_error_string.restype = C.c_char_p
         L.ss2d_error_string.argtypes = [C.c_int]
+        L.ss2d_scan_ckpt_floats.restype = _i64
+        L.ss2d_scan_ckpt_floats.argtypes = [_i64, _i64, _i64, _i64]
         sigs = {n: [_vp, _vp] for n in ("ss2d_selective_scan_fwd", "ss2d_selective_scan_bwd", "ss2d_cross_scan_fwd",
                                         "ss2d_cross_scan_bwd")}
         sigs.update({n: [_vp, _vp, _i64, _i64, _i64, _i64, _i32, _vp] for n in ("ss2d_cross_scan", "ss2d_cross_merge")})
@@ -84,7 +86,7 @@ def lib():
             fn = getattr(L, name)  # AttributeError here == a symbol of include/ss2d_b200.h is not exported
             fn.restype = C.c_int
             fn.argtypes = argtypes
-        if L.ss2d_abi_version() != 1:
+        if L.ss2d_abi_version() != 2:
             raise RuntimeError("libss2d_b200.so ABI version mismatch")
         _lib = L
     return _lib

@@ -7,8 +7,15 @@
 extern "C" int ss2d_abi_version(void) { return SS2D_ABI_VERSION; }
 
 extern "C" const char *ss2d_build_info(void) {
-    return "libss2d_b200 abi=1 arch=sm_100a kernels=scan_fwd,scan_bwd,cross_scan,cross_merge,cross_scan_fused,dwconv_silu,merge_norm_gate "
+    return "libss2d_b200 abi=2 arch=sm_100a kernels=scan_sl_fwd,scan_sl_bwd,scan_fwd,scan_bwd,cross_scan,cross_merge,cross_scan_fused,dwconv_silu,merge_norm_gate "
            "cuda=" SS2D_STR(__CUDACC_VER_MAJOR__) "." SS2D_STR(__CUDACC_VER_MINOR__);
+}
+
+extern "C" int64_t ss2d_scan_ckpt_floats(int64_t batch, int64_t dim, int64_t seqlen, int64_t dstate) {
+    if (batch <= 0 || dim <= 0 || seqlen <= 0 || dstate <= 0) return 0;
+    const int64_t coarse = batch * dim * ((seqlen + SS2D_CKPT_STEPS - 1) / SS2D_CKPT_STEPS) * dstate;
+    const int64_t fine = dstate == 16 ? batch * dim * ((seqlen + SS2D_SL_BLOCK - 1) / SS2D_SL_BLOCK) * dstate : 0;
+    return fine > coarse ? fine : coarse;  // one size serves whichever kernel family takes the shape
 }
 
 extern "C" const char *ss2d_error_string(int code) {

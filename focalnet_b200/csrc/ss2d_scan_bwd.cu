@@ -16,6 +16,7 @@
 // reference issues one scalar atomic per channel per element, 805 M at the microbench).
 #include "ss2d_common.cuh"
 #include "ss2d_scan_tile.cuh"
+#include "ss2d_scan_sl.cuh"
 #include "../../include/ss2d_b200.h"
 #include <cstdlib>
 #include <cstring>
@@ -413,7 +414,8 @@ extern "C" int ss2d_selective_scan_bwd(const ss2d_scan_bwd_params *pp, void *str
     if (p.z && (!pb.dz || !p.out)) return SS2D_EINVAL;
     if (p.out_dtype != SS2D_F32 && p.out_dtype != p.in_dtype) return SS2D_EDTYPE;
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-    if (!p.ckpt && p.seqlen > SS2D_CKPT_STEPS) {
+    const bool state_lanes = ss2d::sl::supported(p);
+    if (!p.ckpt && p.seqlen > (state_lanes ? SS2D_SL_BLOCK : SS2D_CKPT_STEPS)) {
         // Foreign caller that only kept the reference's coarse x: rebuild the fine checkpoints with a
         // states-only forward sweep (out == NULL) into the caller's scratch buffer.
         if (!pb.ckpt_scratch) return SS2D_EINVAL;
@@ -424,6 +426,7 @@ extern "C" int ss2d_selective_scan_bwd(const ss2d_scan_bwd_params *pp, void *str
         if (rc != 0) return rc;
         pb.f.ckpt = pb.ckpt_scratch;
     }
+    if (state_lanes) return ss2d::sl::launch_bwd(pb, s);
     using namespace ss2d;
     constexpr int T = SS2D_BWD_T, NW = SS2D_BWD_NW, MINB = SS2D_BWD_MINB;
     switch (p.in_dtype) {

@@ -16,6 +16,7 @@
 // instructions: every shared-memory operand is [one base register + compile-time immediate].
 #include "ss2d_common.cuh"
 #include "ss2d_scan_tile.cuh"
+#include "ss2d_scan_sl.cuh"
 #include "../../include/ss2d_b200.h"
 
 namespace ss2d {
@@ -269,6 +270,7 @@ extern "C" int ss2d_selective_scan_fwd(const ss2d_scan_fwd_params *pp, void *str
     if (p.z && !p.out_z) return SS2D_EINVAL;
     if (p.batch * p.ngroups * (p.dim / p.ngroups) > 0x7fffffffLL) return SS2D_EINVAL;
     if (p.out_dtype != SS2D_F32 && p.out_dtype != p.in_dtype) return SS2D_EDTYPE;
+    if (ss2d::sl::supported(p)) return ss2d::sl::launch_fwd(p, reinterpret_cast<cudaStream_t>(stream));
     return ss2d::dispatch_fwd<false>(p, reinterpret_cast<cudaStream_t>(stream), ss2d::CrossInfo{0, 0});
 }
 

@@ -85,35 +85,36 @@ def _n_ref(L):
     return (L + _lib.REF_CHUNK - 1) // _lib.REF_CHUNK
 
 
-def _n_fine(L):
-    return (L + _lib.CKPT_STEPS - 1) // _lib.CKPT_STEPS
+def _n_ckpt(batch, dim, L, N):
+    """fp32 elements of the library's checkpoint workspace for this shape (layout private to the library)."""
+    return int(_lib.lib().ss2d_scan_ckpt_floats(batch, dim, L, N))
 
 
 def _alloc_x_ckpt(u, batch, dim, L, N):
-    """One fp32 buffer = [ x (batch,dim,n_ref,2N) | ckpt (batch,dim,n_fine,N) | 1 pad word ].
+    """One fp32 buffer = [ x (batch,dim,n_ref,2N) | ckpt workspace | 1 pad word ].
 
     ``x`` is the contiguous leading view, so callers that only know the reference contract
     (``last_state = x[:, :, -1, 1::2]``, test_selective_scan.py:79) see exactly the reference tensor, while
-    ``scan_bwd`` can find the fine checkpoints behind it (``_ckpt_of``) even when ``x`` travelled through the
+    ``scan_bwd`` can find the checkpoints behind it (``_ckpt_of``) even when ``x`` travelled through the
     reference's own autograd Function (ITS/models/vmamba_layers.py:184,190)."""
-    nx, nc = batch * dim * _n_ref(L) * 2 * N, batch * dim * _n_fine(L) * N
+    nx, nc = batch * dim * _n_ref(L) * 2 * N, _n_ckpt(batch, dim, L, N)
     buf = torch.empty(nx + nc + 1, device=u.device, dtype=torch.float32)  # odd size = the signature _ckpt_of checks
     x = buf[:nx].view(batch, dim, _n_ref(L), 2 * N)
-    ckpt = buf[nx:nx + nc].view(batch, dim, _n_fine(L), N)
+    ckpt = buf[nx:nx + nc]
     return x, ckpt
 
 
 def _ckpt_of(x: Optional[torch.Tensor], batch, dim, L, N):
     if x is None or x.dtype != torch.float32 or not x.is_cuda:
         return None
-    nx, nc = batch * dim * _n_ref(L) * 2 * N, batch * dim * _n_fine(L) * N
+    nx, nc = batch * dim * _n_ref(L) * 2 * N, _n_ckpt(batch, dim, L, N)
     if x.storage_offset() != 0 or x.numel() != nx or not x.is_contiguous():
         return None
     if x.untyped_storage().nbytes() != (nx + nc + 1) * 4:
         return None
     # the odd-sized storage (x | ckpt | 1 tag word) is the signature; no device read, hence no host sync
     flat = torch.as_strided(x, (nx + nc + 1,), (1,), 0)
-    return flat[nx:nx + nc].view(batch, dim, _n_fine(L), N)
+    return flat[nx:nx + nc]
 
 
 def scan_fwd(u, delta, A, B, C, D=None, delta_bias=None, delta_softplus=False, nrows=1, out_float=True, z=None):
@@ -157,8 +158,8 @@ def scan_bwd(u, delta, A, B, C, D, delta_bias, dout, x=None, delta_softplus=Fals
     if ckpt is None:
         ckpt = _ckpt_of(x, batch, dim, L, N)
     scratch = None
-    if ckpt is None and L > _lib.CKPT_STEPS:
-        scratch = torch.empty((batch, dim, _n_fine(L), N), device=u.device, dtype=torch.float32)
+    if ckpt is None and L > _lib.SL_BLOCK:
+        scratch = torch.empty(_n_ckpt(batch, dim, L, N), device=u.device, dtype=torch.float32)
     du, ddelta = torch.empty_like(u, memory_format=torch.contiguous_format), torch.empty_like(delta, memory_format=torch.contiguous_format)
     # the accumulated gradients share ONE zero-filled fp32 buffer (one memset instead of five)
     n_bc, n_a = batch * G * N * L, dim * N

@@ -20,7 +20,7 @@ import torch
 import torch.nn.functional as F
 
 from . import _lib
-from .selective_scan import _DT, C_byref, _chk, _n_fine, _ptr, _stream, build_selective_scan_fn, scan_bwd, scan_fwd
+from .selective_scan import _DT, C_byref, _chk, _n_ckpt, _ptr, _stream, build_selective_scan_fn, scan_bwd, scan_fwd
 
 
 # --------------------------------------------------------------------------------------------- S2
@@ -146,7 +146,7 @@ class FusedCrossScanFn(torch.autograd.Function):
         Ds = None if Ds is None else Ds.contiguous().float()
         delta_bias = None if delta_bias is None else delta_bias.contiguous().float()
         y = torch.zeros((B, D, L), device=x.device, dtype=torch.float32)
-        ckpt = torch.empty((B, 4 * D, _n_fine(L), N), device=x.device, dtype=torch.float32)
+        ckpt = torch.empty(_n_ckpt(B, 4 * D, L, N), device=x.device, dtype=torch.float32)
         P = _lib.CrossFwdParams()
         FusedCrossScanFn._fill(P, x, delta, A, Bs, Cs, Ds, delta_bias, delta_softplus, (B, D, H, W, N))
         P.y, P.ckpt = y.data_ptr(), ckpt.data_ptr()

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define SS2D_ABI_VERSION 1
+#define SS2D_ABI_VERSION 2
 
 /* element types of u / delta / B / C / z (in_dtype) and of out / dout (out_dtype) */
 enum { SS2D_F32 = 0, SS2D_F16 = 1, SS2D_BF16 = 2 };
@@ -47,7 +47,8 @@ enum {
 
 #define SS2D_MAX_DSTATE 256 /* selective_scan_oflex.cpp:192 */
 #define SS2D_REF_CHUNK 2048 /* selective_scan_oflex.cpp:218: x has ceil(L/2048) checkpoints          */
-#define SS2D_CKPT_STEPS 256 /* granularity of this library's own fine checkpoints (see `ckpt`)       */
+#define SS2D_CKPT_STEPS 256 /* checkpoint spacing of the general (warp-scan) kernels, any dstate      */
+#define SS2D_SL_BLOCK 16    /* checkpoint spacing of the state-lanes kernels (dstate == 16)          */
 
 /* ---------------------------------------------------------------------------------------------
  * selective scan, scan-order operands (seam S1)
@@ -58,8 +59,10 @@ enum {
  *   out      : (batch, dim, seqlen)   out_dtype, contiguous rows (stride given)
  *   x        : (batch, dim, ceil(seqlen/2048), 2*dstate) f32 contiguous — (running prod a, h) at the
  *              end of every 2048-step chunk, exactly the reference's checkpoint tensor; may be NULL
- *   ckpt     : (batch, dim, ceil(seqlen/256), dstate) f32 contiguous or NULL — h at the END of every
- *              256-step chunk; the backward recomputes chunk interiors from it
+ *   ckpt     : f32 workspace of ss2d_scan_ckpt_floats() elements, or NULL — the states h the backward restarts
+ *              its recomputation from.  The layout is private to the library (it depends on which kernel
+ *              family serves the shape): dstate == 16 -> (batch, ceil(seqlen/16), dim, 16), h at the end of
+ *              every 16-step block; otherwise (batch, dim, ceil(seqlen/256), dstate), h every 256 steps
  *   out_z    : (batch, dim, seqlen) out_dtype, only with z: out_z = out * silu(z) (out stays un-gated)
  * ------------------------------------------------------------------------------------------- */
 typedef struct ss2d_scan_fwd_params {
@@ -81,8 +84,8 @@ typedef struct ss2d_scan_fwd_params {
 } ss2d_scan_fwd_params;
 
 /*   dout     : (batch, dim, seqlen) out_dtype, last stride 1
- *   ckpt     : fine checkpoints written by the forward, or NULL together with x == the reference
- *              tensor (then the library rebuilds the fine checkpoints in `ckpt_scratch` first)
+ *   ckpt     : the workspace written by the forward, or NULL together with x == the reference
+ *              tensor (then the library rebuilds the checkpoints in `ckpt_scratch` first)
  *   du, ddelta : (batch, dim, seqlen) in_dtype contiguous ; dz likewise (only with z; needs out)
  *   dA (dim,dstate), dD, ddelta_bias (dim) : f32, MUST BE ZEROED by the caller (accumulated over batch)
  *   dB, dC   : (batch, ngroups, dstate, seqlen) f32 contiguous, MUST BE ZEROED (accumulated over the
@@ -91,7 +94,7 @@ typedef struct ss2d_scan_bwd_params {
     ss2d_scan_fwd_params f; /* the forward operands (out/out_z unused unless z != NULL: then f.out = un-gated out) */
     const void *dout;
     int64_t dout_bstride, dout_dstride;
-    float *ckpt_scratch; /* (batch, dim, ceil(seqlen/256), dstate) f32, required when f.ckpt == NULL and seqlen > 256 */
+    float *ckpt_scratch; /* ss2d_scan_ckpt_floats() f32 elements, required when f.ckpt == NULL and seqlen > SS2D_SL_BLOCK */
     void *du, *ddelta, *dz;
     float *dA, *dB, *dC, *dD, *ddelta_bias;
 } ss2d_scan_bwd_params;
@@ -101,6 +104,9 @@ int ss2d_abi_version(void);
 const char *ss2d_build_info(void);
 /* human-readable text for a return code of this library (negative) or of CUDA (positive) */
 const char *ss2d_error_string(int code);
+
+/* number of f32 elements of the `ckpt` workspace for a scan of this shape (0 on invalid sizes) */
+int64_t ss2d_scan_ckpt_floats(int64_t batch, int64_t dim, int64_t seqlen, int64_t dstate);
 
 int ss2d_selective_scan_fwd(const ss2d_scan_fwd_params *p, void *stream);
 int ss2d_selective_scan_bwd(const ss2d_scan_bwd_params *p, void *stream);
@@ -127,7 +133,7 @@ int ss2d_cross_permute(const void *src, void *dst, int64_t B, int64_t C, int64_t
  *   A (4*D,dstate), Dskip (4*D), delta_bias (4*D) : f32, channel index k*D+d (vmamba_layers.py:273-279)
  *   y      : (batch, D, H*W) f32, SPATIAL order, = CrossMerge of the four scans; MUST BE ZEROED by the caller
  *            (each direction accumulates with red.global.add.f32, so the sum order is not deterministic)
- *   ckpt   : (batch, 4*D, ceil(L/256), dstate) f32 — h every 256 scan steps, consumed by the backward
+ *   ckpt   : ss2d_scan_ckpt_floats(batch, 4*D, H*W, dstate) f32 elements, consumed by the backward
  * ------------------------------------------------------------------------------------------- */
 typedef struct ss2d_cross_fwd_params {
     int64_t batch, D, H, W, dstate;

@@ -22,13 +22,17 @@ def lib():
 def test_every_declared_symbol_is_exported(lib):
     from focalnet_b200 import _lib
     src = open(HEADER).read()
-    declared = set(re.findall(r"^(?:int|const char \*)\s*(ss2d_\w+)\(", src, flags=re.M))
+    declared = set(re.findall(r"^(?:int|int64_t|const char \*)\s*(ss2d_\w+)\(", src, flags=re.M))
     assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.ss2d_abi_version() == 1
+    assert lib.ss2d_abi_version() == 2
     assert b"sm_100a" in lib.ss2d_build_info()
     assert b"invalid" in lib.ss2d_error_string(-22)
+    # checkpoint workspace: state-lanes layout (h every 16 steps) for dstate 16, coarse layout otherwise
+    assert lib.ss2d_scan_ckpt_floats(2, 8, 100, 16) == 2 * 8 * 7 * 16
+    assert lib.ss2d_scan_ckpt_floats(2, 8, 1000, 4) == 2 * 8 * 4 * 4
+    assert lib.ss2d_scan_ckpt_floats(0, 8, 1000, 4) == 0
 
 
 def test_struct_layout_matches_header(lib):

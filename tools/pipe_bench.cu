@@ -73,6 +73,30 @@ template <int R> __global__ void k_mix(float *out, float seed) {
     float s = 0; for (int i = 0; i < ILP; ++i) s += v[i] + w[i];
     if (s == 123.456f) out[0] = s;
 }
+// packed fp32 (sm_100): FFMA2 / FMUL2 on register pairs
+__global__ void k_ffma2(float *out, float seed) {
+    float2 v[ILP]; float2 a = make_float2(seed, seed * 0.9f), b = make_float2(seed * 0.5f, seed * 0.4f);
+#pragma unroll
+    for (int i = 0; i < ILP; ++i) v[i] = make_float2(seed + i, seed - i);
+    for (int it = 0; it < ITERS; ++it) {
+#pragma unroll
+        for (int i = 0; i < ILP; ++i) v[i] = __ffma2_rn(v[i], a, b);
+    }
+    float s = 0; for (int i = 0; i < ILP; ++i) s += v[i].x + v[i].y;
+    if (s == 123.456f) out[0] = s;
+}
+// 1 FFMA2 + 1 FFMA + 1 MUFU interleaved (the state-lanes inner loop's mix)
+__global__ void k_mix2(float *out, float seed) {
+    float2 v[ILP]; float w[ILP], u[ILP]; float2 a = make_float2(seed, seed * 0.9f), b = make_float2(seed * 0.5f, seed * 0.4f);
+#pragma unroll
+    for (int i = 0; i < ILP; ++i) { v[i] = make_float2(seed + i, seed - i); w[i] = seed * 0.1f + i * 1e-3f; u[i] = seed + i; }
+    for (int it = 0; it < ITERS; ++it) {
+#pragma unroll
+        for (int i = 0; i < ILP; ++i) { v[i] = __ffma2_rn(v[i], a, b); w[i] = ex2(w[i]); u[i] = fmaf(u[i], a.x, b.x); }
+    }
+    float s = 0; for (int i = 0; i < ILP; ++i) s += v[i].x + v[i].y + w[i] + u[i];
+    if (s == 123.456f) out[0] = s;
+}
 __global__ void k_shfl(float *out, float seed) {
     float v[ILP];
 #pragma unroll
@@ -141,6 +165,8 @@ int main() {
     rep("mix 4 FFMA : 1 MUFU (total)", time_ms([&] { k_mix<4><<<blocks, threads>>>(out, 0.5f); }), 5);
     rep("mix 6 FFMA : 1 MUFU (total)", time_ms([&] { k_mix<6><<<blocks, threads>>>(out, 0.5f); }), 7);
     rep("mix 8 FFMA : 1 MUFU (total)", time_ms([&] { k_mix<8><<<blocks, threads>>>(out, 0.5f); }), 9);
+    rep("FFMA2 (packed, per instr)", time_ms([&] { k_ffma2<<<blocks, threads>>>(out, 0.5f); }), 1);
+    rep("mix FFMA2+FFMA+MUFU (total)", time_ms([&] { k_mix2<<<blocks, threads>>>(out, 0.5f); }), 3);
     rep("SHFL.UP", time_ms([&] { k_shfl<<<blocks, threads>>>(out, 0.5f); }), 1);
     rep("LDS.128 (conflict-free)", time_ms([&] { k_lds128<<<blocks, threads>>>(out, 0.5f); }), 1);
     // reductions: 64 MB window (fits L2), 16 M threads x reps
