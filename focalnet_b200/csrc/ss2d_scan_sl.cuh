@@ -164,6 +164,50 @@ template <typename T, int TT, int NT> struct RowStager {
     }
 };
 
+// Flattened per-thread copy list of one pipeline stage for the FAST kernels (every row 16-byte aligned and
+// L % 16 == 0: a 16-byte piece is never ragged).  All arrays of a stage are laid end to end as 16-byte pieces and
+// dealt round-robin to the CTA's threads; a stage then costs NCOPY predicated cp.async + NCOPY pointer bumps per
+// thread, with no per-array loop and no address arithmetic.
+template <int NT, int NCOPY> struct CopyList {
+    const unsigned char *src[NCOPY];  // global address of this thread's j-th piece in the NEXT stage to issue
+    uint32_t dst[NCOPY];              // shared address inside ring slot 0; 0 = no copy
+    int adv[NCOPY];                   // bytes the source moves from one stage to the next (signed)
+    int base;
+    __device__ __forceinline__ void clear() {
+        base = 0;
+#pragma unroll
+        for (int j = 0; j < NCOPY; ++j) { src[j] = nullptr; dst[j] = 0; adv[j] = 0; }
+    }
+    // rows x TTs steps of `g` (row stride g_rstride), first stage at step t_first, following stages stage_step steps on
+    template <typename T>
+    __device__ __forceinline__ void add(T *smem_rows, int rs_elems, const T *g, int64_t g_rstride, int nrows, int rows_valid, int TTs,
+                                        int perm_sn, int t_first, int stage_step) {
+        constexpr int per = 16 / (int)sizeof(T);
+        const int PPR = TTs / per;
+#pragma unroll
+        for (int j = 0; j < NCOPY; ++j) {
+            const int local = (int)threadIdx.x + j * NT - base;
+            if (local >= 0 && local < nrows * PPR) {
+                const int r = local / PPR, q = local % PPR;
+                if (r < rows_valid) {
+                    const int row = perm_sn ? (r % perm_sn) * (kN / perm_sn) + r / perm_sn : r;
+                    src[j] = reinterpret_cast<const unsigned char *>(g + (int64_t)r * g_rstride + q * per + t_first);
+                    dst[j] = smem_u32(smem_rows + row * rs_elems + q * per);
+                    adv[j] = stage_step * (int)sizeof(T);
+                }
+            }
+        }
+        base += nrows * PPR;
+    }
+    __device__ __forceinline__ void issue(int slot_off) {
+#pragma unroll
+        for (int j = 0; j < NCOPY; ++j) {
+            if (dst[j]) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst[j] + slot_off), "l"(src[j]) : "memory");
+            src[j] += adv[j];
+        }
+    }
+};
+
 // Transposed reduction over the LPC lanes of a channel: y[16] per-step partial sums in, the lane's OWN finished
 // steps [OWN*ng, OWN*ng+OWN) out.  16 - OWN shuffles for 16 sums (a butterfly per value would need 16 * log2 LPC).
 template <int LPC> __device__ __forceinline__ void reduce_lanes(const float (&y)[BK], float (&r)[BK / LPC], int ng) {

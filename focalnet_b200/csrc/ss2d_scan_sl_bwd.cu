@@ -16,6 +16,7 @@
 // (state, 4 steps) leaves the CTA (the reference issues one scalar atomic per channel per element).  Sums over the
 // 16 states (du, ddelta) are transposed reductions over the channel's lanes.
 #include "ss2d_scan_sl.cuh"
+#include <cstdlib>
 
 namespace ss2d {
 namespace sl {
@@ -100,6 +101,27 @@ sl_bwd_kernel(const ss2d_scan_bwd_params pb, const int tiles_per_group, const Fl
     st_C.init(reinterpret_cast<in_t *>(smem + SM::C_off), SM::RSB, reinterpret_cast<const in_t *>(p.C) + b * p.C_bstride + g * p.C_gstride,
               p.C_nstride, kN, kN, fl.vec_bc, SN);
 
+    // FAST: one flattened copy list instead of the five stagers
+    constexpr int NPIECE = (2 * CPC + 2 * kN) * (BK * (int)sizeof(in_t) / 16) + CPC * (BK * (int)sizeof(out_t) / 16);
+    constexpr int NCOPY = (NPIECE + NT - 1) / NT;
+    CopyList<NT, NCOPY> cl;
+    if constexpr (FAST) {
+        const int t_first = ((int)((p.seqlen + BK - 1) / BK) - 1) * BK;
+        cl.clear();
+        cl.add(reinterpret_cast<in_t *>(smem + SM::u_off), SM::RSU, reinterpret_cast<const in_t *>(p.u) + b * p.u_bstride + row0 * p.u_dstride,
+               p.u_dstride, CPC, rows_valid, BK, 0, t_first, -BK);
+        cl.add(reinterpret_cast<in_t *>(smem + SM::d_off), SM::RSU,
+               reinterpret_cast<const in_t *>(p.delta) + b * p.delta_bstride + row0 * p.delta_dstride, p.delta_dstride, CPC, rows_valid, BK, 0,
+               t_first, -BK);
+        cl.add(reinterpret_cast<out_t *>(smem + SM::g_off), SM::RSG,
+               reinterpret_cast<const out_t *>(pb.dout) + b * pb.dout_bstride + row0 * pb.dout_dstride, pb.dout_dstride, CPC, rows_valid, BK, 0,
+               t_first, -BK);
+        cl.add(reinterpret_cast<in_t *>(smem + SM::B_off), SM::RSB, reinterpret_cast<const in_t *>(p.B) + b * p.B_bstride + g * p.B_gstride,
+               p.B_nstride, kN, kN, BK, SN, t_first, -BK);
+        cl.add(reinterpret_cast<in_t *>(smem + SM::C_off), SM::RSB, reinterpret_cast<const in_t *>(p.C) + b * p.C_bstride + g * p.C_gstride,
+               p.C_nstride, kN, kN, BK, SN, t_first, -BK);
+    }
+
     const in_t *z_row = p.z ? reinterpret_cast<const in_t *>(p.z) + b * p.z_bstride + c * p.z_dstride : nullptr;
     const out_t *pre_row = p.z ? reinterpret_cast<const out_t *>(p.out) + b * p.out_bstride + c * p.out_dstride : nullptr;
     const int64_t row = ((int64_t)b * p.dim + c) * L;
@@ -143,30 +165,35 @@ sl_bwd_kernel(const ss2d_scan_bwd_params pb, const int tiles_per_group, const Fl
     for (int i = threadIdx.x; i < NSTAGE * SM::stage_bytes / 16; i += NT) reinterpret_cast<float4 *>(smem)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     __syncthreads();
 
-    auto issue = [&](int k) {  // tile of block k -> ring slot k % NSTAGE (an empty group when k < 0)
+    auto issue = [&](int k, int slot_off) {  // tile of block k -> ring slot at slot_off (an empty group when k < 0)
         if (k >= 0) {
-            const int off = (k % NSTAGE) * SM::stage_bytes, t0 = k * BK;
-            st_u.issue(t0, L, off);
-            st_d.issue(t0, L, off);
-            st_g.issue(t0, L, off);
-            st_B.issue(t0, L, off);
-            st_C.issue(t0, L, off);
+            if constexpr (FAST) {
+                cl.issue(slot_off);
+            } else {
+                const int t0 = k * BK;
+                st_u.issue(t0, L, slot_off);
+                st_d.issue(t0, L, slot_off);
+                st_g.issue(t0, L, slot_off);
+                st_B.issue(t0, L, slot_off);
+                st_C.issue(t0, L, slot_off);
+            }
         }
         cp_async_commit();
     };
-    auto load_ck = [&](int j) {  // h at the right edge of block j (zero left of the sequence)
+    const float *ck_ptr = ck + (int64_t)(nblk - 2) * ck_step;  // walks left one block per load
+    auto load_ck = [&](bool exists) {  // next checkpoint to the left (zero left of the sequence)
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (j >= 0) {
-            const float *ptr = ck + (int64_t)j * ck_step;
-            if constexpr (SN == 4) v = __ldg(reinterpret_cast<const float4 *>(ptr));
-            else { const float2 t = __ldg(reinterpret_cast<const float2 *>(ptr)); v.x = t.x; v.y = t.y; }
+        if (exists) {
+            if constexpr (SN == 4) v = __ldg(reinterpret_cast<const float4 *>(ck_ptr));
+            else { const float2 t = __ldg(reinterpret_cast<const float2 *>(ck_ptr)); v.x = t.x; v.y = t.y; }
         }
+        ck_ptr -= ck_step;
         return v;
     };
     // this lane's OWN steps of block k: softplus, delta*u, (gated) dout -> exchange buffer k & 1
     const int own_u = (warp * CPW + cw) * SM::RSU + OWN * ng, own_g = (warp * CPW + cw) * SM::RSG + OWN * ng;
-    auto prepare = [&](int k, float (&uv)[OWN], float (&dl)[OWN], float (&gv)[OWN]) {
-        const unsigned char *sbuf = smem + ((k + NSTAGE) % NSTAGE) * SM::stage_bytes;
+    auto prepare = [&](int k, int slot_off, int xoff, float (&uv)[OWN], float (&dl)[OWN], float (&gv)[OWN]) {
+        const unsigned char *sbuf = smem + slot_off;
         float dv[OWN], du[OWN];
         lds_k<in_t, OWN>(reinterpret_cast<const in_t *>(sbuf + SM::d_off) + own_u, dv);
         lds_k<in_t, OWN>(reinterpret_cast<const in_t *>(sbuf + SM::u_off) + own_u, uv);
@@ -195,7 +222,7 @@ sl_bwd_kernel(const ss2d_scan_bwd_params pb, const int tiles_per_group, const Fl
             gv[i] = in ? gv[i] : 0.f;
             du[i] = dl[i] * uv[i];
         }
-        float *dst = xpub + (k & 1) * (XBUF * 4);
+        float *dst = xpub + xoff * 4;
         if constexpr (OWN == 4) {
             *reinterpret_cast<float4 *>(dst) = make_float4(dl[0], dl[1], dl[2], dl[3]);
             *reinterpret_cast<float4 *>(dst + NQ * CPW * 4) = make_float4(du[0], du[1], du[2], du[3]);
@@ -207,6 +234,8 @@ sl_bwd_kernel(const ss2d_scan_bwd_params pb, const int tiles_per_group, const Fl
         }
     };
     // dB / dC of a finished block: sum the staged products over the CTA's channels, one vector reduction per (state, 4 steps)
+#pragma unroll
+    for (int i = 0; i < OPT; ++i) red_dst[i] += (int64_t)nblk * BK;  // one block right of the last: walks left per call
     auto reduce_bc = [&](int k) {
 #pragma unroll
         for (int i = 0; i < OPT; ++i) {
@@ -220,7 +249,8 @@ sl_bwd_kernel(const ss2d_scan_bwd_params pb, const int tiles_per_group, const Fl
                     hi = __fadd2_rn(hi, make_float2(v.z, v.w));
                 }
             }
-            float *dst = red_dst[i] + k * BK;
+            red_dst[i] -= BK;
+            float *dst = red_dst[i];
             if (FAST) {
                 red_add_v4(dst, lo.x, lo.y, hi.x, hi.y);
             } else {
@@ -237,6 +267,7 @@ sl_bwd_kernel(const ss2d_scan_bwd_params pb, const int tiles_per_group, const Fl
         }
     };
     // du, ddelta of a finished block: sums over the 16 states, every lane finishes its own steps
+    in_t *du_ptr = du_row + (int64_t)nblk * BK + OWN * ng, *dd_ptr = dd_row + (int64_t)nblk * BK + OWN * ng;  // walk left per call
     auto finalize = [&](int k, const float2 (&sacc)[BK / 2], const float2 (&wacc)[BK / 2], const float (&uv)[OWN], const float (&dl)[OWN],
                         const float (&gv)[OWN], bool store) {
         float sv[BK], wv[BK], s4[OWN], w4[OWN];
@@ -261,14 +292,20 @@ sl_bwd_kernel(const ss2d_scan_bwd_params pb, const int tiles_per_group, const Fl
             dD_acc = fmaf(gv[i], uv[i], dD_acc);
         }
         if (store) {
-            stg_k<in_t, OWN>(du_row + t_own, duo, FAST ? OWN : valid, FAST ? true : fl.vec_grad);
-            stg_k<in_t, OWN>(dd_row + t_own, ddo, FAST ? OWN : valid, FAST ? true : fl.vec_grad);
+            stg_k<in_t, OWN>(du_ptr, duo, FAST ? OWN : valid, FAST ? true : fl.vec_grad);
+            stg_k<in_t, OWN>(dd_ptr, ddo, FAST ? OWN : valid, FAST ? true : fl.vec_grad);
         }
+        du_ptr -= BK;
+        dd_ptr -= BK;
     };
 
     // ---- prologue: tiles of the two rightmost blocks, softplus of the rightmost ----
-    issue(nblk - 1);
-    issue(nblk - 2);
+    int slot0 = ((nblk - 1) % NSTAGE) * SM::stage_bytes;  // ring slots of blocks k, k-1, k-2 (byte offsets), rotated per iteration
+    int slot1 = ((nblk + 1) % NSTAGE) * SM::stage_bytes;  // (k-1) mod 3 == (k+2) mod 3
+    int slot2 = (nblk % NSTAGE) * SM::stage_bytes;        // (k-2) mod 3 == (k+1) mod 3
+    int xcur = ((nblk - 1) & 1) * XBUF;                   // exchange buffer (float4 index) of block k; block k-1 uses the other
+    issue(nblk - 1, slot0);
+    issue(nblk - 2, slot1);
     cp_async_wait<0>();
     __syncthreads();
     float uv_c[OWN], dl_c[OWN], gv_c[OWN];  // own values of the block whose F/R runs in the current iteration
@@ -278,24 +315,24 @@ sl_bwd_kernel(const ss2d_scan_bwd_params pb, const int tiles_per_group, const Fl
     for (int j = 0; j < BK / 2; ++j) { sacc[j] = make_float2(0.f, 0.f); wacc[j] = make_float2(0.f, 0.f); }
 #pragma unroll
     for (int i = 0; i < OWN; ++i) { uv_p[i] = 0.f; dl_p[i] = 0.f; gv_p[i] = 0.f; }
-    prepare(nblk - 1, uv_c, dl_c, gv_c);
-    float4 hin = load_ck(nblk - 2);
+    prepare(nblk - 1, slot0, xcur, uv_c, dl_c, gv_c);
+    float4 hin = load_ck(nblk >= 2);
     __syncthreads();
 
     for (int k = nblk - 1; k >= 0; --k) {
-        issue(k - 2);  // ring slot of block k+1, free since the barrier that ended iteration k+1
-        const float4 hin_next = load_ck(k - 2);
+        issue(k - 2, slot2);  // ring slot of block k+1, free since the barrier that ended iteration k+1
+        const float4 hin_next = load_ck(k >= 2);
         // ---- block k+1: dB/dC sums, du / ddelta (first iteration: all-zero dummies, nothing stored) ----
         if (k + 1 < nblk) reduce_bc(k + 1);
         finalize(k + 1, sacc, wacc, uv_p, dl_p, gv_p, active && k + 1 < nblk);
         // ---- block k-1: softplus of this lane's own steps ----
         float uv_n[OWN], dl_n[OWN], gv_n[OWN];
-        prepare(k - 1, uv_n, dl_n, gv_n);
+        prepare(k - 1, slot1, xcur ^ XBUF, uv_n, dl_n, gv_n);
         // ---- F(k): recompute a_t and h_t of the block ----
-        const unsigned char *buf = smem + (k % NSTAGE) * SM::stage_bytes;
+        const unsigned char *buf = smem + slot0;
         const in_t *sB = reinterpret_cast<const in_t *>(buf + SM::B_off) + ng * SM::RSB;
         const in_t *sC = reinterpret_cast<const in_t *>(buf + SM::C_off) + ng * SM::RSB;
-        const float4 *xc = xq + (k & 1) * XBUF;
+        const float4 *xc = xq + xcur;
         float hcur[SN];
         hcur[0] = hin.x; hcur[1] = hin.y;
         if constexpr (SN == 4) { hcur[2] = hin.z; hcur[3] = hin.w; }
@@ -371,6 +408,8 @@ sl_bwd_kernel(const ss2d_scan_bwd_params pb, const int tiles_per_group, const Fl
             uv_c[i] = uv_n[i]; dl_c[i] = dl_n[i]; gv_c[i] = gv_n[i];
         }
         hin = hin_next;
+        { const int t = slot0; slot0 = slot1; slot1 = slot2; slot2 = t; }
+        xcur ^= XBUF;
         cp_async_wait<0>();  // the tile of block k-2 (issued at the top) has landed for this thread ...
         __syncthreads();     // ... and for everyone; block k's staged dB / dC products are complete
     }
@@ -423,7 +462,14 @@ static int launch_bwd_t(const ss2d_scan_bwd_params &pb, cudaStream_t stream) {
 }
 
 template <typename in_t, typename out_t> static int launch_bwd_sn(const ss2d_scan_bwd_params &pb, cudaStream_t s) {
-    return states_per_lane(pb.f) == 4 ? launch_bwd_t<in_t, out_t, 4>(pb, s) : launch_bwd_t<in_t, out_t, 2>(pb, s);
+    // 2 states per lane at every size: with 4 the a_t / h_t history of a block needs 128 registers and the dB/dC staging
+    // area 64 KB, which leaves one CTA per SM (measured 15.7 ms vs 10.8 ms at B=32, L=16384); the 4-state build stays
+    // reachable through the development switch SS2D_SL_SN=4
+    static const bool force4 = [] {
+        const char *e = getenv("SS2D_SL_SN");
+        return e && atoi(e) == 4;
+    }();
+    return force4 ? launch_bwd_t<in_t, out_t, 4>(pb, s) : launch_bwd_t<in_t, out_t, 2>(pb, s);
 }
 
 int launch_bwd(const ss2d_scan_bwd_params &pb, cudaStream_t s) {

@@ -76,6 +76,23 @@ sl_fwd_kernel(const ss2d_scan_fwd_params p, const int tiles_per_group, const Fla
     st_C.init(reinterpret_cast<in_t *>(smem + SM::C_off), SM::RSB, reinterpret_cast<const in_t *>(p.C) + b * p.C_bstride + g * p.C_gstride,
               p.C_nstride, kN, kN, fl.vec_bc, SN);
 
+    // FAST: one flattened copy list instead of the four stagers
+    constexpr int NPIECE = (2 * CPC + 2 * kN) * (TT * (int)sizeof(in_t) / 16);
+    constexpr int NCOPY = (NPIECE + NT - 1) / NT;
+    CopyList<NT, NCOPY> cl;
+    if constexpr (FAST) {
+        cl.clear();
+        cl.add(reinterpret_cast<in_t *>(smem + SM::u_off), SM::RSU, reinterpret_cast<const in_t *>(p.u) + b * p.u_bstride + row0 * p.u_dstride,
+               p.u_dstride, CPC, rows_valid, TT, 0, 0, TT);
+        cl.add(reinterpret_cast<in_t *>(smem + SM::d_off), SM::RSU,
+               reinterpret_cast<const in_t *>(p.delta) + b * p.delta_bstride + row0 * p.delta_dstride, p.delta_dstride, CPC, rows_valid, TT, 0, 0,
+               TT);
+        cl.add(reinterpret_cast<in_t *>(smem + SM::B_off), SM::RSB, reinterpret_cast<const in_t *>(p.B) + b * p.B_bstride + g * p.B_gstride,
+               p.B_nstride, kN, kN, TT, SN, 0, TT);
+        cl.add(reinterpret_cast<in_t *>(smem + SM::C_off), SM::RSB, reinterpret_cast<const in_t *>(p.C) + b * p.C_bstride + g * p.C_gstride,
+               p.C_nstride, kN, kN, TT, SN, 0, TT);
+    }
+
     const in_t *z_row = p.z ? reinterpret_cast<const in_t *>(p.z) + b * p.z_bstride + c * p.z_dstride : nullptr;
     out_t *o_row = p.out ? reinterpret_cast<out_t *>(p.out) + b * p.out_bstride + c * p.out_dstride : nullptr;
     out_t *oz_row = p.out_z ? reinterpret_cast<out_t *>(p.out_z) + b * p.out_bstride + c * p.out_dstride : nullptr;
@@ -103,10 +120,17 @@ sl_fwd_kernel(const ss2d_scan_fwd_params p, const int tiles_per_group, const Fla
 
     auto issue = [&](int st) {
         const int off = (st % NSTAGE) * SM::stage_bytes, t0 = st * TT;
-        st_u.issue(t0, L, off);
-        st_d.issue(t0, L, off);
-        st_B.issue(t0, L, off);
-        st_C.issue(t0, L, off);
+        if constexpr (FAST) {
+            // the last stage may be short (L % TT != 0): whole 16-byte pieces past L read the next row / batch, or run
+            // off the tensor — copy it with the bounds-checked stagers instead
+            if (t0 + TT <= L) cl.issue(off);
+            else { st_u.issue(t0, L, off); st_d.issue(t0, L, off); st_B.issue(t0, L, off); st_C.issue(t0, L, off); }
+        } else {
+            st_u.issue(t0, L, off);
+            st_d.issue(t0, L, off);
+            st_B.issue(t0, L, off);
+            st_C.issue(t0, L, off);
+        }
         cp_async_commit();
     };
     // this lane's OWN steps of block `blk` (tile of stage `sbuf`, block kb inside it): softplus, delta*u -> exchange buffer
@@ -307,7 +331,12 @@ static int launch_fwd_t(const ss2d_scan_fwd_params &p, cudaStream_t stream) {
 }
 
 template <typename in_t, typename out_t> static int launch_fwd_sn(const ss2d_scan_fwd_params &p, cudaStream_t s) {
-    return states_per_lane(p) == 4 ? launch_fwd_t<in_t, out_t, 4>(p, s) : launch_fwd_t<in_t, out_t, 2>(p, s);
+    static const int tt = [] {
+        const char *e = getenv("SS2D_SL_TT");  // development switch
+        return e ? atoi(e) : 0;
+    }();
+    if (states_per_lane(p) == 4) return tt == 64 ? launch_fwd_t<in_t, out_t, 4, 4, 64>(p, s) : launch_fwd_t<in_t, out_t, 4, 4, 32>(p, s);
+    return tt == 32 ? launch_fwd_t<in_t, out_t, 2, 4, 32>(p, s) : launch_fwd_t<in_t, out_t, 2, 4, 64>(p, s);
 }
 
 int launch_fwd(const ss2d_scan_fwd_params &p, cudaStream_t s) {

@@ -59,6 +59,10 @@ CASES = [
     (1, 12, 1, 1024, 4, torch.float32, True, True, False, True),       # N = 1 (the reference test grid)
     (1, 4, 20, 300, 1, torch.float32, True, True, False, True),        # N > 16
     (3, 10, 8, 1, 2, torch.float32, True, True, False, True),          # L = 1
+    (1, 8, 16, 4112, 1, torch.float32, True, True, False, True),       # aligned fast path with a short last stage
+    (4, 4800, 16, 80, 4, torch.float32, True, True, False, True),      # large batch*dim: 4 states per lane forward, ragged channel tile
+    (2, 9480, 16, 77, 2, torch.bfloat16, True, True, False, True),     # same, unaligned rows, 16-bit
+    (2, 40, 16, 160, 4, torch.float16, True, True, True, False),       # z gate, fp16, no softplus
 ]
 
 
