@@ -249,7 +249,7 @@ def main():
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    dom, dom_ms, dom_bytes = ("scan_bwd_kernel", bwd_ms, bb) if bwd_ms >= fwd_ms else ("scan_fwd_kernel", fwd_ms, fb)
+    dom, dom_ms, dom_bytes = ("sl_bwd_kernel", bwd_ms, bb) if bwd_ms >= fwd_ms else ("sl_fwd_kernel", fwd_ms, fb)
     achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650 (B200_PROFILING.md)",
@@ -257,7 +257,9 @@ def main():
                 "fwd": {"ms": fwd_ms, "GBps": fb / fwd_ms / 1e6, "frac": fb / fwd_ms / 1e6 / peak},
                 "bwd": {"ms": bwd_ms, "GBps": bb / bwd_ms / 1e6, "frac": bb / bwd_ms / 1e6 / peak},
                 "fwd_bwd_frac": (fb + bb) / (fwd_ms + bwd_ms) / 1e6 / peak,
-                "note": "host launch gap included in each event pair; kernel is FMA-issue/MUFU bound, see DESIGN.md"}
+                "note": "host launch gap included in each event pair; the state-lanes kernels are bound by the shared-memory "
+                        "pipe (63-69 %) and instruction issue, not by HBM: see DESIGN.md §4 and profiles/; `traffic` exceeds the "
+                        "algorithmic bytes by the per-16-step checkpoints (100.7 MB written by fwd, read by bwd)"}
     traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(traffic_file):
         try:
