@@ -41,7 +41,7 @@ class CrossFwdParams(C.Structure):
         [(n, _i64) for n in ("batch", "D", "H", "W", "dstate")]
         + [("in_dtype", _i32), ("delta_softplus", _i32)]
         + [(n, _vp) for n in ("x", "delta", "B", "C", "A", "Dskip", "delta_bias", "y", "ckpt")]
-        + [("bc_bstride", _i64), ("bc_gstride", _i64)]
+        + [("bc_bstride", _i64), ("bc_gstride", _i64), ("work", _vp)]
     )
 
 
@@ -50,7 +50,8 @@ class CrossBwdParams(C.Structure):
                                                              "dDskip", "ddelta_bias")]
 
 
-EXPORTS = ("ss2d_abi_version", "ss2d_build_info", "ss2d_error_string", "ss2d_scan_ckpt_floats", "ss2d_selective_scan_fwd",
+EXPORTS = ("ss2d_abi_version", "ss2d_build_info", "ss2d_error_string", "ss2d_scan_ckpt_floats", "ss2d_cross_work_floats",
+           "ss2d_plane_transpose", "ss2d_selective_scan_fwd",
            "ss2d_selective_scan_bwd", "ss2d_cross_scan", "ss2d_cross_merge", "ss2d_cross_scan_fwd",
            "ss2d_cross_scan_bwd", "ss2d_dwconv_silu_fwd", "ss2d_dwconv_silu_bwd", "ss2d_merge_norm_gate_fwd",
            "ss2d_merge_norm_gate_bwd", "ss2d_cross_permute")
@@ -73,11 +74,14 @@ def lib():
         L.ss2d_error_string.argtypes = [C.c_int]
         L.ss2d_scan_ckpt_floats.restype = _i64
         L.ss2d_scan_ckpt_floats.argtypes = [_i64, _i64, _i64, _i64]
+        L.ss2d_cross_work_floats.restype = _i64
+        L.ss2d_cross_work_floats.argtypes = [_i64, _i64, _i64, _i64, _i64, _i32, _i32]
         sigs = {n: [_vp, _vp] for n in ("ss2d_selective_scan_fwd", "ss2d_selective_scan_bwd", "ss2d_cross_scan_fwd",
                                         "ss2d_cross_scan_bwd")}
         sigs.update({n: [_vp, _vp, _i64, _i64, _i64, _i64, _i32, _vp] for n in ("ss2d_cross_scan", "ss2d_cross_merge")})
         sigs["ss2d_dwconv_silu_fwd"] = [_vp, _i64, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _vp]
         sigs["ss2d_dwconv_silu_bwd"] = [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _i64, _i64, _i64, _i64, _vp]
+        sigs["ss2d_plane_transpose"] = [_vp, _vp, _i64, _i64, _i64, _i32, _vp]
         sigs["ss2d_cross_permute"] = [_vp, _vp, _i64, _i64, _i64, _i64, _i32, _i32, _vp]
         _f32 = C.c_float
         sigs["ss2d_merge_norm_gate_fwd"] = [_vp, _vp, _vp, _f32, _vp, _i64, _vp, _i64, _i64, _i64, _vp]

@@ -1,6 +1,7 @@
 // ss2d_abi.cu — version / diagnostics entry points of libss2d_b200.so (see include/ss2d_b200.h).
 #include <cuda_runtime.h>
 #include "../../include/ss2d_b200.h"
+#include "ss2d_scan_sl.cuh"
 #define SS2D_STR_(x) #x
 #define SS2D_STR(x) SS2D_STR_(x)
 
@@ -16,6 +17,15 @@ extern "C" int64_t ss2d_scan_ckpt_floats(int64_t batch, int64_t dim, int64_t seq
     const int64_t coarse = batch * dim * ((seqlen + SS2D_CKPT_STEPS - 1) / SS2D_CKPT_STEPS) * dstate;
     const int64_t fine = dstate == 16 ? batch * dim * ((seqlen + SS2D_SL_BLOCK - 1) / SS2D_SL_BLOCK) * dstate : 0;
     return fine > coarse ? fine : coarse;  // one size serves whichever kernel family takes the shape
+}
+
+extern "C" int64_t ss2d_cross_work_floats(int64_t batch, int64_t D, int64_t H, int64_t W, int64_t dstate, int32_t in_dtype,
+                                          int32_t backward) {
+    if (batch <= 0 || D <= 0 || H <= 0 || W <= 0 || in_dtype != SS2D_F32 || (H * W) % SS2D_SL_BLOCK != 0) return 0;
+    ss2d_scan_fwd_params p{};
+    p.batch = batch; p.dim = 4 * D; p.seqlen = H * W; p.dstate = dstate; p.ngroups = 4;
+    if (!ss2d::sl::supported(p)) return 0;
+    return (backward ? 3 : 2) * batch * D * H * W;
 }
 
 extern "C" const char *ss2d_error_string(int code) {

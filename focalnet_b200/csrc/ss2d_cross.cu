@@ -193,6 +193,53 @@ static int cross_dispatch(bool merge, const void *in, void *out, int64_t B, int6
     }
 }
 
+// src: planes of (H, W) -> dst: planes of (W, H), dst = src^T or dst += src^T.  The fused seam on the state-lanes
+// kernels walks directions 1 / 3 over x^T (and accumulates their outputs into y^T), so that every direction reads and
+// writes CONTIGUOUS runs: one transposed copy of the 192-row x, not the reference's 4x (B,4,D,L) tensor.
+template <bool ACC>
+__global__ void __launch_bounds__(kTile *kRows) plane_transpose_kernel(const float *__restrict__ src, float *__restrict__ dst, int H, int W) {
+    __shared__ float tile[kTile][kTile + 1];
+    const int tiles_w = (W + kTile - 1) / kTile, tiles_h = (H + kTile - 1) / kTile;
+    const int64_t plane = blockIdx.x / (tiles_w * tiles_h);
+    const int tile_id = blockIdx.x % (tiles_w * tiles_h);
+    const int h0 = (tile_id / tiles_w) * kTile, w0 = (tile_id % tiles_w) * kTile;
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const float *s = src + plane * (int64_t)H * W;
+    float *d = dst + plane * (int64_t)H * W;
+#pragma unroll
+    for (int r = 0; r < kTile; r += kRows) {
+        const int h = h0 + ty + r, w = w0 + tx;
+        if (h < H && w < W) tile[ty + r][tx] = s[(int64_t)h * W + w];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < kTile; r += kRows) {
+        const int w = w0 + ty + r, h = h0 + tx;
+        if (h < H && w < W) {
+            float *q = d + (int64_t)w * H + h;
+            if (ACC) *q += tile[tx][ty + r];
+            else *q = tile[tx][ty + r];
+        }
+    }
+}
+
+int plane_transpose(const float *src, float *dst, int64_t planes, int H, int W, bool acc, cudaStream_t stream) {
+    const int64_t tiles = (int64_t)((W + kTile - 1) / kTile) * ((H + kTile - 1) / kTile);
+    if (planes * tiles > 0x7fffffffLL) return SS2D_EINVAL;
+    const dim3 blk(kTile, kRows);
+    if (acc) plane_transpose_kernel<true><<<(unsigned)(planes * tiles), blk, 0, stream>>>(src, dst, H, W);
+    else plane_transpose_kernel<false><<<(unsigned)(planes * tiles), blk, 0, stream>>>(src, dst, H, W);
+    return (int)cudaGetLastError();
+}
+
+}  // namespace ss2d
+
+extern "C" int ss2d_plane_transpose(const float *src, float *dst, int64_t planes, int64_t H, int64_t W, int32_t accumulate, void *stream) {
+    if (!src || !dst || planes <= 0 || H <= 0 || W <= 0 || H > 0x7fffffffLL || W > 0x7fffffffLL) return SS2D_EINVAL;
+    return ss2d::plane_transpose(src, dst, planes, (int)H, (int)W, accumulate != 0, reinterpret_cast<cudaStream_t>(stream));
+}
+
+namespace ss2d {
 }  // namespace ss2d
 
 extern "C" int ss2d_cross_scan(const void *x, void *xs, int64_t B, int64_t C, int64_t H, int64_t W, int32_t dtype, void *stream) {

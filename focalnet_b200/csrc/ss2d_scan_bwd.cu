@@ -29,6 +29,8 @@
 
 namespace ss2d {
 
+int plane_transpose(const float *src, float *dst, int64_t planes, int H, int W, bool acc, cudaStream_t stream);  // ss2d_cross.cu
+
 struct BwdFlags {
     bool vec_u, vec_delta, vec_bc, vec_dout, vec_z, vec_out, vec_dbc, vec_grad;
 };
@@ -467,6 +469,23 @@ extern "C" int ss2d_cross_scan_bwd(const ss2d_cross_bwd_params *pp, void *stream
     using namespace ss2d;
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     const CrossInfo xi{(int)c.H, (int)c.W};
+    {
+        ss2d_scan_fwd_params q = p;  // the forward's view of the problem decides the kernel family (checkpoint layout)
+        q.out_bstride = c.D * L; q.out_dstride = L;
+        if (c.work && ss2d::sl::cross_covered(q)) {
+            if (!p.ckpt && L > SS2D_SL_BLOCK) return SS2D_EINVAL;
+            const int64_t n = c.batch * c.D * L;
+            float *xT = c.work, *dyT = c.work + n, *dxT = c.work + 2 * n;
+            int rc = ss2d::plane_transpose(reinterpret_cast<const float *>(c.x), xT, c.batch * c.D, (int)c.H, (int)c.W, false, s);
+            if (rc == 0) rc = ss2d::plane_transpose(pp->dy, dyT, c.batch * c.D, (int)c.H, (int)c.W, false, s);
+            if (rc != 0) return rc;
+            cudaError_t e = cudaMemsetAsync(dxT, 0, (size_t)n * sizeof(float), s);
+            if (e != cudaSuccess) return (int)e;
+            rc = ss2d::sl::launch_cross_bwd(pb, ss2d::sl::CrossAux{xT, dyT, dxT}, s);
+            if (rc != 0) return rc;
+            return ss2d::plane_transpose(dxT, pp->dx, c.batch * c.D, (int)c.W, (int)c.H, true, s);
+        }
+    }
     if (!p.ckpt && L > SS2D_CKPT_STEPS) return SS2D_EINVAL;  // the fused backward needs the forward's checkpoints
     constexpr int T = SS2D_BWD_T, NW = SS2D_BWD_NW, MINB = SS2D_BWD_MINB;
     switch (c.in_dtype) {

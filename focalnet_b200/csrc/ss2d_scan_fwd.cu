@@ -21,6 +21,8 @@
 
 namespace ss2d {
 
+int plane_transpose(const float *src, float *dst, int64_t planes, int H, int W, bool acc, cudaStream_t stream);  // ss2d_cross.cu
+
 struct FwdFlags {
     bool vec_u, vec_delta, vec_bc, vec_out, vec_z;
 };
@@ -293,5 +295,18 @@ extern "C" int ss2d_cross_scan_fwd(const ss2d_cross_fwd_params *pp, void *stream
     p.B_nstride = p.C_nstride = L;
     p.out = c.y; p.out_bstride = c.D * L; p.out_dstride = L;
     p.ckpt = c.ckpt;
+    if (c.work && ss2d::sl::cross_covered(p)) {
+        // state-lanes kernels: directions 1 / 3 over x^T, their outputs into y^T, folded back into y at the end
+        cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+        const int64_t n = c.batch * c.D * L;
+        float *xT = c.work, *yT = c.work + n;
+        int rc = ss2d::plane_transpose(reinterpret_cast<const float *>(c.x), xT, c.batch * c.D, (int)c.H, (int)c.W, false, s);
+        if (rc != 0) return rc;
+        cudaError_t e = cudaMemsetAsync(yT, 0, (size_t)n * sizeof(float), s);
+        if (e != cudaSuccess) return (int)e;
+        rc = ss2d::sl::launch_cross_fwd(p, ss2d::sl::CrossAux{xT, nullptr, yT}, s);
+        if (rc != 0) return rc;
+        return ss2d::plane_transpose(yT, c.y, c.batch * c.D, (int)c.W, (int)c.H, true, s);
+    }
     return ss2d::dispatch_fwd<true>(p, reinterpret_cast<cudaStream_t>(stream), ss2d::CrossInfo{(int)c.H, (int)c.W});
 }

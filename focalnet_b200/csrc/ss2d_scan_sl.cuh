@@ -208,6 +208,93 @@ template <int NT, int NCOPY> struct CopyList {
     }
 };
 
+// ---- fused seam S3: CrossScan / CrossMerge as addressing ----------------------------------------------------
+// Direction k maps scan step l to a pixel of the (H, W) plane (vmamba_layers.py:35-37):
+//   k=0: l   k=1: (l % H) * W + l / H   k=2: L-1-l   k=3: with m = L-1-l: (m % H) * W + m / H
+// DirWalk keeps the pixel offset of one scan step and moves it by whole strides without divisions.
+struct DirWalk {
+    int k, H, W, h, w, lin;
+    __device__ __forceinline__ void init(int k_, int H_, int W_, int L, int l) {
+        k = k_; H = H_; W = W_;
+        const int m = (k & 2) ? L - 1 - l : l;
+        lin = m;
+        w = m / H_;  // floor also for negative m (never dereferenced there)
+        h = m - w * H_;
+        if (h < 0) { h += H_; --w; }
+    }
+    __device__ __forceinline__ void advance(int d) {  // l += d
+        const int dm = (k & 2) ? -d : d;
+        lin += dm;
+        if (k & 1) {  // column walks only (the state-lanes fused path uses the linear directions on x / x^T)
+            h += dm;
+            while (h >= H) { h -= H; ++w; }
+            while (h < 0) { h += H; --w; }
+        }
+    }
+    __device__ __forceinline__ int off() const { return (k & 1) ? h * W + w : lin; }
+};
+
+// Element-wise (4-byte cp.async) gather of `u` / `dout` rows from spatial-order fp32 planes into a tile in SCAN
+// order.  A thread owns one step position e of the tile and rows r0, r0+RSTEP, ...: one DirWalk per thread.
+template <int NT, int TTs, int NROW> struct GatherList {
+    static_assert(NT % TTs == 0, "threads must tile the steps of a stage");
+    static constexpr int RSTEP = NT / TTs;
+    static constexpr int NG = (NROW + RSTEP - 1) / RSTEP;
+    const float *src;   // plane of row r0
+    int64_t row_step;   // elements between this thread's rows
+    uint32_t dst;       // shared address of (row r0, e) in ring slot 0
+    int dst_step, nrow, l;  // nrow: rows this thread copies; l: scan step of its element in the NEXT stage to issue
+    DirWalk walk;
+    __device__ __forceinline__ void init(float *smem_rows, int rs_elems, const float *plane0, int64_t plane_stride, int rows_valid, int k,
+                                         int H, int W, int L, int t_first) {
+        const int e = threadIdx.x % TTs, r0 = threadIdx.x / TTs;
+        src = plane0 + (int64_t)r0 * plane_stride;
+        row_step = (int64_t)RSTEP * plane_stride;
+        dst = smem_u32(smem_rows + r0 * rs_elems + e);
+        dst_step = RSTEP * rs_elems * 4;
+        nrow = r0 < rows_valid ? (rows_valid - r0 + RSTEP - 1) / RSTEP : 0;
+        l = t_first + e;
+        walk.init(k, H, W, L, l);
+    }
+    // copy this thread's element of every row for the stage it points at, then move `stage_step` steps on
+    __device__ __forceinline__ void issue(int slot_off, int L, int stage_step) {
+        if (l < L && l >= 0) {
+            const float *s = src + walk.off();
+            uint32_t d = dst + slot_off;
+#pragma unroll
+            for (int j = 0; j < NG; ++j) {
+                if (j < nrow) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(d), "l"(s) : "memory");
+                s += row_step;
+                d += dst_step;
+            }
+        }
+        l += stage_step;
+        walk.advance(stage_step);
+    }
+};
+
+// Accumulate OWN consecutive scan steps starting at `walk` into a spatial-order fp32 plane (CrossMerge / CrossScan^T
+// as a store).  k = 0 / 2: the steps are adjacent pixels -> one vector reduction; k = 1 / 3: a column walk.
+template <int OWN> __device__ __forceinline__ void red_own_cross(float *plane, const DirWalk &walk, const float (&v)[OWN]) {
+    if (!(walk.k & 1)) {
+        float *dst = plane + (walk.k == 0 ? walk.lin : walk.lin - (OWN - 1));
+        if constexpr (OWN == 4) {
+            if (walk.k == 0) red_add_v4(dst, v[0], v[1], v[2], v[3]);
+            else red_add_v4(dst, v[3], v[2], v[1], v[0]);
+        } else {
+            const float a = walk.k == 0 ? v[0] : v[1], b = walk.k == 0 ? v[1] : v[0];
+            asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(dst), "f"(a), "f"(b) : "memory");
+        }
+    } else {
+        DirWalk t = walk;
+#pragma unroll
+        for (int i = 0; i < OWN; ++i) {
+            red_add_f32(plane + t.off(), v[i]);
+            t.advance(1);
+        }
+    }
+}
+
 // Transposed reduction over the LPC lanes of a channel: y[16] per-step partial sums in, the lane's OWN finished
 // steps [OWN*ng, OWN*ng+OWN) out.  16 - OWN shuffles for 16 sums (a butterfly per value would need 16 * log2 LPC).
 template <int LPC> __device__ __forceinline__ void reduce_lanes(const float (&y)[BK], float (&r)[BK / LPC], int ng) {
@@ -237,6 +324,18 @@ bool supported(const ss2d_scan_fwd_params &p);
 int states_per_lane(const ss2d_scan_fwd_params &p);
 int launch_fwd(const ss2d_scan_fwd_params &p, cudaStream_t stream);
 int launch_bwd(const ss2d_scan_bwd_params &p, cudaStream_t stream);
+// fused seam S3 (u / out resp. u / dout / du are spatial-order fp32 planes, groups = the 4 directions).
+// cross_covered(): fp32, dstate 16, L % 16 == 0 and 16-byte aligned x / delta / B / C — a rule both the forward and the
+// backward can evaluate (they must pick the same kernel family: the checkpoint layouts differ); everything else runs on
+// the warp-scan kernels.  The output / gradient buffers of a covered problem must be 16-byte aligned (SS2D_ESTRIDE).
+// Directions 1 / 3 use the TRANSPOSED planes: uT / doutT = x^T / dy^T (inputs), accT = y^T (forward) or dx^T (backward).
+struct CrossAux {
+    const float *uT, *doutT;
+    float *accT;
+};
+bool cross_covered(const ss2d_scan_fwd_params &p);
+int launch_cross_fwd(const ss2d_scan_fwd_params &p, const CrossAux &aux, cudaStream_t stream);
+int launch_cross_bwd(const ss2d_scan_bwd_params &p, const CrossAux &aux, cudaStream_t stream);
 
 }  // namespace sl
 }  // namespace ss2d

@@ -53,9 +53,14 @@ template <typename in_t, typename out_t, int SN, int NW> struct BwdSmem {
 //   barrier  (everyone is done reading the staging area)
 //   [ R(k): dx chain, gradient products, staging of dB/dC ]
 //   barrier  (staging complete; the tile of block k-1 has landed)
-template <typename in_t, typename out_t, int SN, int NW, bool FAST>
+// CROSS (fused seam S3, FAST only): u and dout are read from the fp32 planes x[b,d] / dy[b,d] (directions 0 / 2,
+// forwards / backwards) or from their transposed copies aux.uT / aux.doutT (directions 1 / 3); du is accumulated
+// (red.global.add) into dx[b,d] resp. dx^T (aux.accT) — CrossMerge.backward and CrossScan.backward as load / store
+// addressing over contiguous runs.  ddelta, dB, dC stay in scan order.
+template <typename in_t, typename out_t, int SN, int NW, bool FAST, bool CROSS = false>
 __global__ void __launch_bounds__(NW *kWarp, SN == 2 ? 3 : 2)
-sl_bwd_kernel(const ss2d_scan_bwd_params pb, const int tiles_per_group, const Flags fl) {
+sl_bwd_kernel(const ss2d_scan_bwd_params pb, const int tiles_per_group, const Flags fl, const CrossAux aux) {
+    static_assert(!CROSS || (FAST && sizeof(in_t) == 4 && sizeof(out_t) == 4), "fused seam: fp32, aligned, L % 16 == 0");
     using M = Map<SN>;
     using SM = BwdSmem<in_t, out_t, SN, NW>;
     constexpr int NT = NW * kWarp, CPC = SM::CPC, LPC = M::LPC, CPW = M::CPW, OWN = M::OWN, NQ = SM::NQ, NIDX = SM::NIDX;
@@ -86,15 +91,16 @@ sl_bwd_kernel(const ss2d_scan_bwd_params pb, const int tiles_per_group, const Fl
     const float4 *red_all = reinterpret_cast<const float4 *>(smem + SM::red_off);
 
     const int64_t row0 = (int64_t)g * per_g + ch0;
+    const int64_t urow0 = CROSS ? ch0 : row0;  // row of u / dout / du: d in fused mode
     RowStager<in_t, BK, NT> st_u, st_d, st_B, st_C;
     RowStager<out_t, BK, NT> st_g;
-    st_u.init(reinterpret_cast<in_t *>(smem + SM::u_off), SM::RSU, reinterpret_cast<const in_t *>(p.u) + b * p.u_bstride + row0 * p.u_dstride,
+    st_u.init(reinterpret_cast<in_t *>(smem + SM::u_off), SM::RSU, reinterpret_cast<const in_t *>(p.u) + b * p.u_bstride + urow0 * p.u_dstride,
               p.u_dstride, CPC, rows_valid, fl.vec_u, 0);
     st_d.init(reinterpret_cast<in_t *>(smem + SM::d_off), SM::RSU,
               reinterpret_cast<const in_t *>(p.delta) + b * p.delta_bstride + row0 * p.delta_dstride, p.delta_dstride, CPC, rows_valid,
               fl.vec_delta, 0);
     st_g.init(reinterpret_cast<out_t *>(smem + SM::g_off), SM::RSG,
-              reinterpret_cast<const out_t *>(pb.dout) + b * pb.dout_bstride + row0 * pb.dout_dstride, pb.dout_dstride, CPC, rows_valid,
+              reinterpret_cast<const out_t *>(pb.dout) + b * pb.dout_bstride + urow0 * pb.dout_dstride, pb.dout_dstride, CPC, rows_valid,
               fl.vec_dout, 0);
     st_B.init(reinterpret_cast<in_t *>(smem + SM::B_off), SM::RSB, reinterpret_cast<const in_t *>(p.B) + b * p.B_bstride + g * p.B_gstride,
               p.B_nstride, kN, kN, fl.vec_bc, SN);
@@ -102,20 +108,33 @@ sl_bwd_kernel(const ss2d_scan_bwd_params pb, const int tiles_per_group, const Fl
               p.C_nstride, kN, kN, fl.vec_bc, SN);
 
     // FAST: one flattened copy list instead of the five stagers
-    constexpr int NPIECE = (2 * CPC + 2 * kN) * (BK * (int)sizeof(in_t) / 16) + CPC * (BK * (int)sizeof(out_t) / 16);
+    constexpr int NPIECE = CROSS ? (CPC + 2 * kN) * (BK * (int)sizeof(in_t) / 16)
+                                 : (2 * CPC + 2 * kN) * (BK * (int)sizeof(in_t) / 16) + CPC * (BK * (int)sizeof(out_t) / 16);
     constexpr int NCOPY = (NPIECE + NT - 1) / NT;
     CopyList<NT, NCOPY> cl;
+    GatherList<NT, BK, CPC> gu, gg;
+    if constexpr (CROSS) {
+        const int t_first = ((int)((p.seqlen + BK - 1) / BK) - 1) * BK;
+        gu.init(reinterpret_cast<float *>(smem + SM::u_off), SM::RSU,
+                ((g & 1) ? aux.uT : reinterpret_cast<const float *>(p.u)) + b * p.u_bstride + urow0 * p.u_dstride, p.u_dstride, rows_valid,
+                g & 2, 1, 1, (int)p.seqlen, t_first);
+        gg.init(reinterpret_cast<float *>(smem + SM::g_off), SM::RSG,
+                ((g & 1) ? aux.doutT : reinterpret_cast<const float *>(pb.dout)) + b * pb.dout_bstride + urow0 * pb.dout_dstride,
+                pb.dout_dstride, rows_valid, g & 2, 1, 1, (int)p.seqlen, t_first);
+    }
     if constexpr (FAST) {
         const int t_first = ((int)((p.seqlen + BK - 1) / BK) - 1) * BK;
         cl.clear();
-        cl.add(reinterpret_cast<in_t *>(smem + SM::u_off), SM::RSU, reinterpret_cast<const in_t *>(p.u) + b * p.u_bstride + row0 * p.u_dstride,
-               p.u_dstride, CPC, rows_valid, BK, 0, t_first, -BK);
+        if constexpr (!CROSS)
+            cl.add(reinterpret_cast<in_t *>(smem + SM::u_off), SM::RSU, reinterpret_cast<const in_t *>(p.u) + b * p.u_bstride + row0 * p.u_dstride,
+                   p.u_dstride, CPC, rows_valid, BK, 0, t_first, -BK);
         cl.add(reinterpret_cast<in_t *>(smem + SM::d_off), SM::RSU,
                reinterpret_cast<const in_t *>(p.delta) + b * p.delta_bstride + row0 * p.delta_dstride, p.delta_dstride, CPC, rows_valid, BK, 0,
                t_first, -BK);
-        cl.add(reinterpret_cast<out_t *>(smem + SM::g_off), SM::RSG,
-               reinterpret_cast<const out_t *>(pb.dout) + b * pb.dout_bstride + row0 * pb.dout_dstride, pb.dout_dstride, CPC, rows_valid, BK, 0,
-               t_first, -BK);
+        if constexpr (!CROSS)
+            cl.add(reinterpret_cast<out_t *>(smem + SM::g_off), SM::RSG,
+                   reinterpret_cast<const out_t *>(pb.dout) + b * pb.dout_bstride + row0 * pb.dout_dstride, pb.dout_dstride, CPC, rows_valid, BK, 0,
+                   t_first, -BK);
         cl.add(reinterpret_cast<in_t *>(smem + SM::B_off), SM::RSB, reinterpret_cast<const in_t *>(p.B) + b * p.B_bstride + g * p.B_gstride,
                p.B_nstride, kN, kN, BK, SN, t_first, -BK);
         cl.add(reinterpret_cast<in_t *>(smem + SM::C_off), SM::RSB, reinterpret_cast<const in_t *>(p.C) + b * p.C_bstride + g * p.C_gstride,
@@ -125,7 +144,9 @@ sl_bwd_kernel(const ss2d_scan_bwd_params pb, const int tiles_per_group, const Fl
     const in_t *z_row = p.z ? reinterpret_cast<const in_t *>(p.z) + b * p.z_bstride + c * p.z_dstride : nullptr;
     const out_t *pre_row = p.z ? reinterpret_cast<const out_t *>(p.out) + b * p.out_bstride + c * p.out_dstride : nullptr;
     const int64_t row = ((int64_t)b * p.dim + c) * L;
-    in_t *du_row = reinterpret_cast<in_t *>(pb.du) + row;
+    in_t *du_base = reinterpret_cast<in_t *>(pb.du);
+    if constexpr (CROSS) { if (g & 1) du_base = reinterpret_cast<in_t *>(aux.accT); }
+    in_t *du_row = du_base + (CROSS ? ((int64_t)b * per_g + (active ? c_local : per_g - 1)) * L : row);
     in_t *dd_row = reinterpret_cast<in_t *>(pb.ddelta) + row;
     in_t *dz_row = pb.dz ? reinterpret_cast<in_t *>(pb.dz) + row : nullptr;
     const float Dv = p.D ? p.D[c] : 0.f;
@@ -169,6 +190,7 @@ sl_bwd_kernel(const ss2d_scan_bwd_params pb, const int tiles_per_group, const Fl
         if (k >= 0) {
             if constexpr (FAST) {
                 cl.issue(slot_off);
+                if constexpr (CROSS) { gu.issue(slot_off, L, -BK); gg.issue(slot_off, L, -BK); }
             } else {
                 const int t0 = k * BK;
                 st_u.issue(t0, L, slot_off);
@@ -267,6 +289,8 @@ sl_bwd_kernel(const ss2d_scan_bwd_params pb, const int tiles_per_group, const Fl
         }
     };
     // du, ddelta of a finished block: sums over the 16 states, every lane finishes its own steps
+    DirWalk xwalk;  // pixel of this lane's first own step of the next block to be finalised (fused seam only)
+    if constexpr (CROSS) xwalk.init(g & 2, 1, 1, L, nblk * BK + OWN * ng);
     in_t *du_ptr = du_row + (int64_t)nblk * BK + OWN * ng, *dd_ptr = dd_row + (int64_t)nblk * BK + OWN * ng;  // walk left per call
     auto finalize = [&](int k, const float2 (&sacc)[BK / 2], const float2 (&wacc)[BK / 2], const float (&uv)[OWN], const float (&dl)[OWN],
                         const float (&gv)[OWN], bool store) {
@@ -292,9 +316,11 @@ sl_bwd_kernel(const ss2d_scan_bwd_params pb, const int tiles_per_group, const Fl
             dD_acc = fmaf(gv[i], uv[i], dD_acc);
         }
         if (store) {
-            stg_k<in_t, OWN>(du_ptr, duo, FAST ? OWN : valid, FAST ? true : fl.vec_grad);
+            if constexpr (CROSS) red_own_cross<OWN>(reinterpret_cast<float *>(du_row), xwalk, duo);
+            else stg_k<in_t, OWN>(du_ptr, duo, FAST ? OWN : valid, FAST ? true : fl.vec_grad);
             stg_k<in_t, OWN>(dd_ptr, ddo, FAST ? OWN : valid, FAST ? true : fl.vec_grad);
         }
+        if constexpr (CROSS) xwalk.advance(-BK);
         du_ptr -= BK;
         dd_ptr -= BK;
     };
@@ -432,8 +458,8 @@ sl_bwd_kernel(const ss2d_scan_bwd_params pb, const int tiles_per_group, const Fl
     }
 }
 
-template <typename in_t, typename out_t, int SN, int NW = 4>
-static int launch_bwd_t(const ss2d_scan_bwd_params &pb, cudaStream_t stream) {
+template <typename in_t, typename out_t, int SN, int NW = 4, bool CROSS = false>
+static int launch_bwd_t(const ss2d_scan_bwd_params &pb, cudaStream_t stream, CrossAux xi = CrossAux{nullptr, nullptr, nullptr}) {
     using SM = BwdSmem<in_t, out_t, SN, NW>;
     const ss2d_scan_fwd_params &p = pb.f;
     const int per_g = (int)(p.dim / p.ngroups);
@@ -455,10 +481,15 @@ static int launch_bwd_t(const ss2d_scan_bwd_params &pb, cudaStream_t stream) {
     auto go = [&](auto kern) -> int {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM::total);
         if (e != cudaSuccess) return (int)e;
-        kern<<<(unsigned)grid, NW * kWarp, SM::total, stream>>>(pb, tiles, fl);
+        kern<<<(unsigned)grid, NW * kWarp, SM::total, stream>>>(pb, tiles, fl, xi);
         return (int)cudaGetLastError();
     };
-    return fast ? go(sl_bwd_kernel<in_t, out_t, SN, NW, true>) : go(sl_bwd_kernel<in_t, out_t, SN, NW, false>);
+    if constexpr (CROSS) {
+        if (!fast) return SS2D_ESTRIDE;  // covered problem (cross_covered) with a gradient buffer that is not 16-byte aligned
+        return go(sl_bwd_kernel<in_t, out_t, SN, NW, true, true>);
+    } else {
+        return fast ? go(sl_bwd_kernel<in_t, out_t, SN, NW, true>) : go(sl_bwd_kernel<in_t, out_t, SN, NW, false>);
+    }
 }
 
 template <typename in_t, typename out_t> static int launch_bwd_sn(const ss2d_scan_bwd_params &pb, cudaStream_t s) {
@@ -483,6 +514,11 @@ int launch_bwd(const ss2d_scan_bwd_params &pb, cudaStream_t s) {
                                            : launch_bwd_sn<__nv_bfloat16, __nv_bfloat16>(pb, s);
         default: return SS2D_EDTYPE;
     }
+}
+
+int launch_cross_bwd(const ss2d_scan_bwd_params &pb, const CrossAux &aux, cudaStream_t s) {
+    if (!aligned16(aux.uT) || !aligned16(aux.doutT) || !aligned16(aux.accT)) return SS2D_ESTRIDE;
+    return launch_bwd_t<float, float, 2, 4, true>(pb, s, aux);
 }
 
 }  // namespace sl

@@ -35,9 +35,13 @@ template <typename in_t, int SN, int NW, int TT> struct FwdSmem {
 // microbench puts only ~2.6 warps on an SM sub-partition): iteration k runs the 16 x SN recurrence steps of block
 // k, the lane reduction + stores of block k-1 and the softplus of block k+1 in one basic block.
 // FAST: every tensor 16-byte aligned and L % 16 == 0 — no tail masks, one predicated vector store per output.
-template <typename in_t, typename out_t, int SN, int NW, int TT, bool FAST>
-__global__ void __launch_bounds__(NW *kWarp)
-sl_fwd_kernel(const ss2d_scan_fwd_params p, const int tiles_per_group, const Flags fl) {
+// CROSS (fused seam S3, FAST only): the groups are the 4 scan directions, `u` is the spatial-order fp32 plane x[b, d]
+// shared by the 4 directions and `out` the merged fp32 plane y[b, d], accumulated with red.global.add (zero-filled).
+// Directions 0 / 2 walk x forwards / backwards; directions 1 / 3 walk the transposed copy x^T (aux.uT) and accumulate
+// into y^T (aux.accT), so every direction moves contiguous runs.  delta / B / C stay in scan order.
+template <typename in_t, typename out_t, int SN, int NW, int TT, bool FAST, bool CROSS>
+__device__ __forceinline__ void sl_fwd_body(const ss2d_scan_fwd_params &p, const int tiles_per_group, const Flags &fl, const CrossAux &aux) {
+    static_assert(!CROSS || (FAST && sizeof(in_t) == 4 && sizeof(out_t) == 4), "fused seam: fp32, aligned, L % 16 == 0");
     using M = Map<SN>;
     using SM = FwdSmem<in_t, SN, NW, TT>;
     constexpr int NT = NW * kWarp, CPC = SM::CPC, LPC = M::LPC, CPW = M::CPW, OWN = M::OWN, NQ = BK / 4, BPS = TT / BK;
@@ -65,8 +69,9 @@ sl_fwd_kernel(const ss2d_scan_fwd_params p, const int tiles_per_group, const Fla
     constexpr int XBUF = 2 * NQ * CPW;  // float4 per buffer
 
     const int64_t row0 = (int64_t)g * per_g + ch0;
+    const int64_t urow0 = CROSS ? ch0 : row0;  // row of u / out: d in fused mode
     RowStager<in_t, TT, NT> st_u, st_d, st_B, st_C;
-    st_u.init(reinterpret_cast<in_t *>(smem + SM::u_off), SM::RSU, reinterpret_cast<const in_t *>(p.u) + b * p.u_bstride + row0 * p.u_dstride,
+    st_u.init(reinterpret_cast<in_t *>(smem + SM::u_off), SM::RSU, reinterpret_cast<const in_t *>(p.u) + b * p.u_bstride + urow0 * p.u_dstride,
               p.u_dstride, CPC, rows_valid, fl.vec_u, 0);
     st_d.init(reinterpret_cast<in_t *>(smem + SM::d_off), SM::RSU,
               reinterpret_cast<const in_t *>(p.delta) + b * p.delta_bstride + row0 * p.delta_dstride, p.delta_dstride, CPC, rows_valid,
@@ -77,13 +82,19 @@ sl_fwd_kernel(const ss2d_scan_fwd_params p, const int tiles_per_group, const Fla
               p.C_nstride, kN, kN, fl.vec_bc, SN);
 
     // FAST: one flattened copy list instead of the four stagers
-    constexpr int NPIECE = (2 * CPC + 2 * kN) * (TT * (int)sizeof(in_t) / 16);
+    constexpr int NPIECE = ((CROSS ? 1 : 2) * CPC + 2 * kN) * (TT * (int)sizeof(in_t) / 16);
     constexpr int NCOPY = (NPIECE + NT - 1) / NT;
     CopyList<NT, NCOPY> cl;
+    GatherList<NT, TT, CPC> gu;
+    if constexpr (CROSS)
+        gu.init(reinterpret_cast<float *>(smem + SM::u_off), SM::RSU,
+                ((g & 1) ? aux.uT : reinterpret_cast<const float *>(p.u)) + b * p.u_bstride + urow0 * p.u_dstride, p.u_dstride, rows_valid,
+                g & 2, 1, 1, (int)p.seqlen, 0);
     if constexpr (FAST) {
         cl.clear();
-        cl.add(reinterpret_cast<in_t *>(smem + SM::u_off), SM::RSU, reinterpret_cast<const in_t *>(p.u) + b * p.u_bstride + row0 * p.u_dstride,
-               p.u_dstride, CPC, rows_valid, TT, 0, 0, TT);
+        if constexpr (!CROSS)
+            cl.add(reinterpret_cast<in_t *>(smem + SM::u_off), SM::RSU, reinterpret_cast<const in_t *>(p.u) + b * p.u_bstride + row0 * p.u_dstride,
+                   p.u_dstride, CPC, rows_valid, TT, 0, 0, TT);
         cl.add(reinterpret_cast<in_t *>(smem + SM::d_off), SM::RSU,
                reinterpret_cast<const in_t *>(p.delta) + b * p.delta_bstride + row0 * p.delta_dstride, p.delta_dstride, CPC, rows_valid, TT, 0, 0,
                TT);
@@ -94,7 +105,10 @@ sl_fwd_kernel(const ss2d_scan_fwd_params p, const int tiles_per_group, const Fla
     }
 
     const in_t *z_row = p.z ? reinterpret_cast<const in_t *>(p.z) + b * p.z_bstride + c * p.z_dstride : nullptr;
-    out_t *o_row = p.out ? reinterpret_cast<out_t *>(p.out) + b * p.out_bstride + c * p.out_dstride : nullptr;
+    const int64_t c_out = CROSS ? (active ? c_local : per_g - 1) : c;
+    out_t *o_base = reinterpret_cast<out_t *>(p.out);
+    if constexpr (CROSS) { if (g & 1) o_base = reinterpret_cast<out_t *>(aux.accT); }
+    out_t *o_row = o_base ? o_base + b * p.out_bstride + c_out * p.out_dstride : nullptr;
     out_t *oz_row = p.out_z ? reinterpret_cast<out_t *>(p.out_z) + b * p.out_bstride + c * p.out_dstride : nullptr;
     const float Dv = p.D ? p.D[c] : 0.f;
     const float bias = p.delta_bias ? p.delta_bias[c] : 0.f;
@@ -124,7 +138,11 @@ sl_fwd_kernel(const ss2d_scan_fwd_params p, const int tiles_per_group, const Fla
             // the last stage may be short (L % TT != 0): whole 16-byte pieces past L read the next row / batch, or run
             // off the tensor — copy it with the bounds-checked stagers instead
             if (t0 + TT <= L) cl.issue(off);
-            else { st_u.issue(t0, L, off); st_d.issue(t0, L, off); st_B.issue(t0, L, off); st_C.issue(t0, L, off); }
+            else {
+                if constexpr (!CROSS) st_u.issue(t0, L, off);
+                st_d.issue(t0, L, off); st_B.issue(t0, L, off); st_C.issue(t0, L, off);
+            }
+            if constexpr (CROSS) gu.issue(off, L, TT);
         } else {
             st_u.issue(t0, L, off);
             st_d.issue(t0, L, off);
@@ -159,6 +177,8 @@ sl_fwd_kernel(const ss2d_scan_fwd_params p, const int tiles_per_group, const Fla
             *reinterpret_cast<float2 *>(dst + NQ * CPW * 4) = make_float2(du[0], du[1]);
         }
     };
+    DirWalk ywalk;  // pixel of this lane's first own step of the NEXT block to be finished (fused seam only)
+    if constexpr (CROSS) ywalk.init(g & 2, 1, 1, L, OWN * ng);
     // lane reduction + stores of a finished block
     auto finish = [&](const float2 (&y2)[BK / 2], const float (&uv)[OWN], int blk, bool store) {
         float y[BK], o[OWN];
@@ -168,7 +188,10 @@ sl_fwd_kernel(const ss2d_scan_fwd_params p, const int tiles_per_group, const Fla
 #pragma unroll
         for (int i = 0; i < OWN; ++i) o[i] = fmaf(Dv, uv[i], o[i]);
         const int t_own = blk * BK + OWN * ng;
-        if constexpr (FAST) {
+        if constexpr (CROSS) {
+            if (store) red_own_cross<OWN>(reinterpret_cast<float *>(o_row), ywalk, o);
+            ywalk.advance(BK);
+        } else if constexpr (FAST) {
             if (store && o_row) stg_k<out_t, OWN>(o_row + t_own, o, OWN, true);
         } else {
             if (store && o_row) stg_k<out_t, OWN>(o_row + t_own, o, L - t_own, fl.vec_out);
@@ -247,6 +270,7 @@ sl_fwd_kernel(const ss2d_scan_fwd_params p, const int tiles_per_group, const Fla
                 ck += ck_step;
             }
             // ---- block blk-1: sum over the 16 states, stores (independent of the recurrence above) ----
+            if constexpr (CROSS) { if (blk == 0) ywalk.advance(-BK); }
             finish(y2_prev, uv_prev, blk - 1, active && blk > 0);
             // ---- block blk+1: softplus of this lane's own steps (the values of a block past the end are never used) ----
             float uv_next[OWN], dls_next;
@@ -276,12 +300,29 @@ sl_fwd_kernel(const ss2d_scan_fwd_params p, const int tiles_per_group, const Fla
     finish(y2_prev, uv_prev, nblk - 1, active);
 }
 
+// two entry points over one body: the fused variant carries the gather state and is capped at 168 registers (3 CTAs per
+// SM); the plain one is left to ptxas (137 registers) — an explicit minimum-blocks bound makes it spend all it is given
+template <typename in_t, typename out_t, int SN, int NW, int TT, bool FAST>
+__global__ void __launch_bounds__(NW *kWarp)
+sl_fwd_kernel(const ss2d_scan_fwd_params p, const int tiles_per_group, const Flags fl) {
+    sl_fwd_body<in_t, out_t, SN, NW, TT, FAST, false>(p, tiles_per_group, fl, CrossAux{nullptr, nullptr, nullptr});
+}
+template <int SN, int NW, int TT>
+__global__ void __launch_bounds__(NW *kWarp, 3)
+sl_fwd_cross_kernel(const ss2d_scan_fwd_params p, const int tiles_per_group, const Flags fl, const CrossAux aux) {
+    sl_fwd_body<float, float, SN, NW, TT, true, true>(p, tiles_per_group, fl, aux);
+}
+
 bool supported(const ss2d_scan_fwd_params &p) {
-    static const int force = [] {
-        const char *e = getenv("SS2D_SCAN_IMPL");  // development switch: "warpscan" forces the general kernels
-        return (e && e[0] == 'w') ? 1 : 0;
-    }();
-    return !force && p.dstate == kN && p.seqlen <= 0x7fffffffLL - 4096;
+    if (p.dstate != kN || p.seqlen > 0x7fffffffLL - 4096) return false;
+    // SS2D_SCAN_IMPL=warpscan / statelanes pins the family (tests, A/B timing); read per call so a test can flip it
+    const char *e = getenv("SS2D_SCAN_IMPL");
+    if (e && e[0] == 'w') return false;
+    if (e && e[0] == 's') return true;
+    // a state-lanes warp walks its whole sequence serially, so the launch takes ~L/4096 * 240 us however few channels
+    // there are; the warp-scan kernels scale with the work and win below ~4.6 k channels (measured: B=1 x 768 channels,
+    // L=19200: 369 us vs 646 us forward; B=8 x 768, L=4096: 305 us vs 237 us)
+    return p.batch * p.dim >= 4608;
 }
 
 int states_per_lane(const ss2d_scan_fwd_params &p) {
@@ -312,8 +353,8 @@ static void fill_flags(const ss2d_scan_fwd_params &p, int64_t ei, int64_t eo, Fl
     fl.vec_z = p.z && aligned16(p.z) && (p.z_bstride * ei) % 16 == 0 && (p.z_dstride * ei) % 16 == 0;
 }
 
-template <typename in_t, typename out_t, int SN, int NW = 4, int TT = 64>
-static int launch_fwd_t(const ss2d_scan_fwd_params &p, cudaStream_t stream) {
+template <typename in_t, typename out_t, int SN, int NW = 4, int TT = 64, bool CROSS = false>
+static int launch_fwd_t(const ss2d_scan_fwd_params &p, cudaStream_t stream, CrossAux xi = CrossAux{nullptr, nullptr, nullptr}) {
     using SM = FwdSmem<in_t, SN, NW, TT>;
     const int per_g = (int)(p.dim / p.ngroups);
     const int tiles = (per_g + SM::CPC - 1) / SM::CPC;
@@ -327,7 +368,16 @@ static int launch_fwd_t(const ss2d_scan_fwd_params &p, cudaStream_t stream) {
         kern<<<(unsigned)grid, NW * kWarp, SM::total, stream>>>(p, tiles, fl);
         return (int)cudaGetLastError();
     };
-    return fast ? go(sl_fwd_kernel<in_t, out_t, SN, NW, TT, true>) : go(sl_fwd_kernel<in_t, out_t, SN, NW, TT, false>);
+    if constexpr (CROSS) {
+        if (!fast) return SS2D_ESTRIDE;  // covered problem (cross_covered) whose y is not 16-byte aligned
+        auto kern = sl_fwd_cross_kernel<SN, NW, TT>;
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM::total);
+        if (e != cudaSuccess) return (int)e;
+        kern<<<(unsigned)grid, NW * kWarp, SM::total, stream>>>(p, tiles, fl, xi);
+        return (int)cudaGetLastError();
+    } else {
+        return fast ? go(sl_fwd_kernel<in_t, out_t, SN, NW, TT, true>) : go(sl_fwd_kernel<in_t, out_t, SN, NW, TT, false>);
+    }
 }
 
 template <typename in_t, typename out_t> static int launch_fwd_sn(const ss2d_scan_fwd_params &p, cudaStream_t s) {
@@ -349,6 +399,20 @@ int launch_fwd(const ss2d_scan_fwd_params &p, cudaStream_t s) {
                                            : launch_fwd_sn<__nv_bfloat16, __nv_bfloat16>(p, s);
         default: return SS2D_EDTYPE;
     }
+}
+
+bool cross_covered(const ss2d_scan_fwd_params &p) {
+    if (!supported(p) || p.in_dtype != SS2D_F32 || p.out_dtype != SS2D_F32 || p.z || p.seqlen % BK != 0) return false;
+    Flags fl{};
+    ss2d_scan_fwd_params q = p;
+    q.out = nullptr; q.out_z = nullptr;  // the rule must not depend on buffers only one of the two passes sees
+    fill_flags(q, 4, 4, fl);
+    return fl.vec_u && fl.vec_delta && fl.vec_bc && (p.out_bstride * 4) % 16 == 0 && (p.out_dstride * 4) % 16 == 0;
+}
+
+int launch_cross_fwd(const ss2d_scan_fwd_params &p, const CrossAux &xi, cudaStream_t s) {
+    if (!aligned16(xi.uT) || !aligned16(xi.accT)) return SS2D_ESTRIDE;
+    return states_per_lane(p) == 4 ? launch_fwd_t<float, float, 4, 4, 32, true>(p, s, xi) : launch_fwd_t<float, float, 2, 4, 64, true>(p, s, xi);
 }
 
 }  // namespace sl

@@ -150,11 +150,21 @@ class FusedCrossScanFn(torch.autograd.Function):
         P = _lib.CrossFwdParams()
         FusedCrossScanFn._fill(P, x, delta, A, Bs, Cs, Ds, delta_bias, delta_softplus, (B, D, H, W, N))
         P.y, P.ckpt = y.data_ptr(), ckpt.data_ptr()
+        work = FusedCrossScanFn._work(x, N, L, backward=False)
+        P.work = _ptr(work)
         with torch.cuda.device(x.device):
             _lib.check(_lib.lib().ss2d_cross_scan_fwd(C_byref(P), _stream(x)), "ss2d_cross_scan_fwd")
         ctx.save_for_backward(x, delta, A, Bs, Cs, Ds, delta_bias, ckpt)
         ctx.delta_softplus = delta_softplus
         return y
+
+    @staticmethod
+    def _work(x, N, L, backward):
+        """Scratch for the state-lanes kernels (x^T | y^T, resp. x^T | dy^T | dx^T); None selects the warp-scan kernels.
+        The library's rule depends only on dtype / sizes, so the forward and the backward of a problem always agree."""
+        B, D, H, W = x.shape
+        n = int(_lib.lib().ss2d_cross_work_floats(B, D, H, W, N, _DT[x.dtype], int(backward)))
+        return torch.empty(n, device=x.device, dtype=torch.float32) if n else None
 
     @staticmethod
     def _fill(P, x, delta, A, Bs, Cs, Ds, delta_bias, delta_softplus, dims):
@@ -181,6 +191,8 @@ class FusedCrossScanFn(torch.autograd.Function):
         P = _lib.CrossBwdParams()
         FusedCrossScanFn._fill(P.f, x, delta, A, Bs, Cs, Ds, delta_bias, ctx.delta_softplus, (B, D, H, W, N))
         P.f.ckpt = ckpt.data_ptr()
+        work = FusedCrossScanFn._work(x, N, L, backward=True)
+        P.f.work = _ptr(work)
         P.dy, P.dx, P.ddelta = dy.data_ptr(), dx.data_ptr(), ddelta.data_ptr()
         P.dA, P.dB, P.dC, P.dDskip, P.ddelta_bias = dA.data_ptr(), dB.data_ptr(), dC.data_ptr(), _ptr(dDs), _ptr(dbias)
         with torch.cuda.device(x.device):
@@ -403,17 +415,21 @@ def smoke_fused():
     import numpy as np
     from oracle import ss2d_oracle as orc
     g = torch.Generator().manual_seed(3)
-    B, D, H, W, N = 1, 8, 6, 10, 16
+    import os
+    B, D, H, W, N = 1, 8, 8, 10, 16
     L = H * W
     x = torch.randn(B, D, H, W, generator=g).cuda()
     delta = (0.5 * torch.rand(B, 4 * D, L, generator=g)).cuda()
     A = (-0.5 * torch.rand(4 * D, N, generator=g)).cuda()
     Bs, Cs = torch.randn(B, 4, N, L, generator=g).cuda(), torch.randn(B, 4, N, L, generator=g).cuda()
     Ds, bias = torch.randn(4 * D, generator=g).cuda(), (0.5 * torch.rand(4 * D, generator=g)).cuda()
-    y = FusedCrossScanFn.apply(x, delta, A, Bs, Cs, Ds, bias, True)
     xs = orc.cross_scan(x).reshape(B, 4 * D, L)
     f = orc.scan_fwd(xs, delta, A, Bs, Cs, Ds, None, bias, True)
     ref = orc.cross_merge(f["out"].reshape(B, 4, D, H, W))
-    err = float(np.abs(y.cpu().numpy() - ref).max() / np.abs(ref).max())
-    print(f"[smoke] fused SS2D core vs CPU oracle: max rel err {err:.2e}")
-    assert err < 1e-3, err
+    for family in ("statelanes", "warpscan"):  # pin each kernel family in turn (the default rule goes by problem size)
+        os.environ["SS2D_SCAN_IMPL"] = family
+        y = FusedCrossScanFn.apply(x, delta, A, Bs, Cs, Ds, bias, True)
+        err = float(np.abs(y.cpu().numpy() - ref).max() / np.abs(ref).max())
+        print(f"[smoke] fused SS2D core ({family}) vs CPU oracle: max rel err {err:.2e}")
+        assert err < 1e-3, err
+    os.environ.pop("SS2D_SCAN_IMPL", None)

@@ -144,13 +144,19 @@ typedef struct ss2d_cross_fwd_params {
     float *ckpt;
     int64_t bc_bstride, bc_gstride; /* element strides of B and C over batch / direction (rows of dstate are L apart);
                                        0 = contiguous.  Lets B, C be views into the permuted x_dbl (no .contiguous() copy) */
+    float *work;                    /* NULL, or scratch of ss2d_cross_work_floats() f32 elements (16-byte aligned).  With it,
+                                       fp32 / dstate 16 / H*W % 16 == 0 problems run on the state-lanes kernels: directions
+                                       1 and 3 walk ONE transposed copy of x (and accumulate into a transposed y that is
+                                       folded back at the end) so that every direction moves contiguous runs.  Pass it to
+                                       the forward AND the backward of a problem, or to neither (the checkpoint layouts of
+                                       the two kernel families differ). */
 } ss2d_cross_fwd_params;
 
 /*   dy : (batch, D, H*W) f32 spatial (gathered per direction = CrossMerge.backward).
  *   dx : (batch, D, H*W) f32 spatial, ZEROED (du of the 4 directions accumulated = CrossScan.backward);
  *   ddelta (batch,4*D,L) in_dtype scan order; dB, dC (batch,4,dstate,L) f32 scan order ZEROED;
- *   dA (4*D,dstate), dDskip, ddelta_bias (4*D) f32 ZEROED.  f.ckpt (from the forward) is required when L > 256;
- *   ckpt_scratch is reserved (must be NULL).                                                              */
+ *   dA (4*D,dstate), dDskip, ddelta_bias (4*D) f32 ZEROED.  f.ckpt (from the forward) is required when L > 256
+ *   (L > 16 with f.work); ckpt_scratch is reserved (must be NULL); f.work: 3*batch*D*H*W f32 elements here. */
 typedef struct ss2d_cross_bwd_params {
     ss2d_cross_fwd_params f;
     const float *dy;
@@ -159,6 +165,12 @@ typedef struct ss2d_cross_bwd_params {
     void *ddelta;
     float *dA, *dB, *dC, *dDskip, *ddelta_bias;
 } ss2d_cross_bwd_params;
+
+/* f32 elements of `work`: 2*batch*D*H*W for the forward, 3*batch*D*H*W for the backward; 0 when the state-lanes
+ * kernels do not take the problem (not fp32, dstate != 16, H*W % 16 != 0, fewer than ~4.6 k channel sequences) */
+int64_t ss2d_cross_work_floats(int64_t batch, int64_t D, int64_t H, int64_t W, int64_t dstate, int32_t in_dtype, int32_t backward);
+/* src: `planes` images of (H, W) -> dst: images of (W, H); dst = src^T, or dst += src^T when accumulate != 0 */
+int ss2d_plane_transpose(const float *src, float *dst, int64_t planes, int64_t H, int64_t W, int32_t accumulate, void *stream);
 
 int ss2d_cross_scan_fwd(const ss2d_cross_fwd_params *p, void *stream);
 int ss2d_cross_scan_bwd(const ss2d_cross_bwd_params *p, void *stream);

@@ -17,3 +17,12 @@ def pytest_configure(config):
 @pytest.fixture(scope="session")
 def golden_dir():
     return GOLDEN
+
+
+@pytest.fixture(params=["statelanes", "warpscan"])
+def scan_family(request, monkeypatch):
+    """Runs a GPU test once per scan-kernel family.  The library picks the family by problem size (state-lanes from
+    ~4.6 k channel sequences of dstate 16, warp-scan otherwise); SS2D_SCAN_IMPL pins it so that the small parity shapes
+    exercise both (shapes a family does not cover, e.g. dstate != 16, fall through to the other one)."""
+    monkeypatch.setenv("SS2D_SCAN_IMPL", request.param)
+    return request.param

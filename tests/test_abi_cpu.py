@@ -33,6 +33,11 @@ def test_every_declared_symbol_is_exported(lib):
     assert lib.ss2d_scan_ckpt_floats(2, 8, 100, 16) == 2 * 8 * 7 * 16
     assert lib.ss2d_scan_ckpt_floats(2, 8, 1000, 4) == 2 * 8 * 4 * 4
     assert lib.ss2d_scan_ckpt_floats(0, 8, 1000, 4) == 0
+    # fused-seam scratch: only fp32 / dstate 16 / L % 16 == 0 / enough channel sequences run on the state-lanes kernels
+    assert lib.ss2d_cross_work_floats(8, 192, 64, 64, 16, 0, 0) == 2 * 8 * 192 * 4096
+    assert lib.ss2d_cross_work_floats(8, 192, 64, 64, 16, 0, 1) == 3 * 8 * 192 * 4096
+    assert lib.ss2d_cross_work_floats(8, 192, 64, 64, 8, 0, 0) == 0 and lib.ss2d_cross_work_floats(8, 192, 64, 64, 16, 2, 0) == 0
+    assert lib.ss2d_cross_work_floats(8, 192, 17, 23, 16, 0, 0) == 0 and lib.ss2d_cross_work_floats(1, 192, 64, 64, 16, 0, 0) == 0
 
 
 def test_struct_layout_matches_header(lib):
@@ -40,7 +45,7 @@ def test_struct_layout_matches_header(lib):
     from focalnet_b200 import _lib
     assert ctypes.sizeof(_lib.ScanFwdParams) == 5 * 8 + 4 * 4 + 8 * 8 + 12 * 8 + 8 + 16 + 8 * 3
     assert ctypes.sizeof(_lib.ScanBwdParams) == ctypes.sizeof(_lib.ScanFwdParams) + 8 + 16 + 8 + 8 * 8
-    assert ctypes.sizeof(_lib.CrossFwdParams) == 5 * 8 + 2 * 4 + 9 * 8 + 2 * 8
+    assert ctypes.sizeof(_lib.CrossFwdParams) == 5 * 8 + 2 * 4 + 9 * 8 + 2 * 8 + 8
     assert ctypes.sizeof(_lib.CrossBwdParams) == ctypes.sizeof(_lib.CrossFwdParams) + 9 * 8
 
 

@@ -12,7 +12,7 @@ import torch
 
 from tests._util import load_ref_cuda, make_scan_inputs, rel_err
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.usefixtures("scan_family")]
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
 SCAN_FILES = sorted(glob.glob(os.path.join(GOLDEN, "scan_*.npz")))
 TOL = {torch.float32: 1e-3, torch.float16: 1e-2, torch.bfloat16: 1e-2}

@@ -10,7 +10,7 @@ import torch
 
 from tests._util import rel_err
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.usefixtures("scan_family")]
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
 
 

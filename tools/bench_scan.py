@@ -36,3 +36,24 @@ for (B, D, H, W, tag) in shapes:
               f"fwd+bwd {(tf+tb)*1e6:8.1f} us {100*(bf+bb)/(tf+tb)/1e9/peak:5.1f}% of {peak:.0f} GB/s")
         del d, a, out, x, ckpt
         torch.cuda.empty_cache()
+
+if "s3" in sys.argv:  # fused seam: CrossScan -> scan -> CrossMerge in one kernel (no 4x copies)
+    from focalnet_b200 import FusedCrossScanFn
+    for (B, D, H, W, tag) in [(8, 192, 64, 64, "micro"), (32, 192, 128, 128, "train-L16384"), (1, 192, 120, 160, "fullres-g4")]:
+        K, N, L = 4, 16, H * W
+        d = make_scan_inputs(B, K * D, N, L, K)
+        g = torch.Generator().manual_seed(0)
+        xx = torch.randn(B, D, H, W, generator=g).cuda()
+        dy = torch.randn(B, D, L, generator=g).cuda()
+        fa = [t.detach().clone().requires_grad_() for t in (xx, d["delta"], d["A"], d["B"], d["C"], d["D"], d["delta_bias"])]
+        tf = timeit(lambda: FusedCrossScanFn.apply(*[t.detach() for t in fa], True))
+        def fb():
+            yy = FusedCrossScanFn.apply(*fa, True); yy.backward(dy)
+        tfb = timeit(fb, n=10)
+        big, bc, pl = B * K * D * L, B * K * N * L, B * D * L
+        bf = 4 * (pl + big + 2 * bc) + 4 * pl
+        bb = 4 * (pl + 2 * big + 2 * bc) + 4 * (2 * pl) + 8 * bc
+        print(f"[{tag} fp32] S3 fused fwd {tf*1e6:8.1f} us ({bf/tf/1e9:7.1f} GB/s {100*bf/tf/1e9/peak:5.1f}%)  fwd+bwd (autograd, incl. zero fills) "
+              f"{tfb*1e6:8.1f} us ({100*(bf+bb)/tfb/1e9/peak:5.1f}%)")
+        del d, fa, xx, dy
+        torch.cuda.empty_cache()
