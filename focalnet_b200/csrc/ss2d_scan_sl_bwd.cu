@@ -58,7 +58,7 @@ template <typename in_t, typename out_t, int SN, int NW> struct BwdSmem {
 // (red.global.add) into dx[b,d] resp. dx^T (aux.accT) — CrossMerge.backward and CrossScan.backward as load / store
 // addressing over contiguous runs.  ddelta, dB, dC stay in scan order.
 template <typename in_t, typename out_t, int SN, int NW, bool FAST, bool CROSS = false>
-__global__ void __launch_bounds__(NW *kWarp, SN == 2 ? 3 : 2)
+__global__ void __launch_bounds__(NW *kWarp, 3)
 sl_bwd_kernel(const ss2d_scan_bwd_params pb, const int tiles_per_group, const Flags fl, const CrossAux aux) {
     static_assert(!CROSS || (FAST && sizeof(in_t) == 4 && sizeof(out_t) == 4), "fused seam: fp32, aligned, L % 16 == 0");
     using M = Map<SN>;
@@ -493,14 +493,14 @@ static int launch_bwd_t(const ss2d_scan_bwd_params &pb, cudaStream_t stream, Cro
 }
 
 template <typename in_t, typename out_t> static int launch_bwd_sn(const ss2d_scan_bwd_params &pb, cudaStream_t s) {
-    // 2 states per lane at every size: with 4 the a_t / h_t history of a block needs 128 registers and the dB/dC staging
-    // area 64 KB, which leaves one CTA per SM (measured 15.7 ms vs 10.8 ms at B=32, L=16384); the 4-state build stays
-    // reachable through the development switch SS2D_SL_SN=4
+    // 2 states per lane at every size: with 4 the a_t / h_t history of a block needs 128 registers (255 per thread) and
+    // the dB/dC staging area 16 KB per warp; measured at B=32, L=16384: 4 warps/CTA 15.7 ms (one CTA per SM), 2 warps/CTA
+    // 9.73 ms, against 9.34 ms for 2 states per lane.  The 4-state build stays reachable through SS2D_SL_SN=4
     static const bool force4 = [] {
         const char *e = getenv("SS2D_SL_SN");
         return e && atoi(e) == 4;
     }();
-    return force4 ? launch_bwd_t<in_t, out_t, 4>(pb, s) : launch_bwd_t<in_t, out_t, 2>(pb, s);
+    return force4 ? launch_bwd_t<in_t, out_t, 4, 2>(pb, s) : launch_bwd_t<in_t, out_t, 2>(pb, s);
 }
 
 int launch_bwd(const ss2d_scan_bwd_params &pb, cudaStream_t s) {
