@@ -33,7 +33,7 @@ extern "C" const char *ss2d_error_string(int code) {
         case SS2D_OK: return "ok";
         case SS2D_EINVAL: return "invalid argument (null pointer, non-positive size, dim % ngroups != 0, dstate > 256)";
         case SS2D_EDTYPE: return "unsupported dtype combination (out/dout must be f32 or equal to the input dtype)";
-        case SS2D_ESTRIDE: return "last-dimension stride must be 1";
+        case SS2D_ESTRIDE: return "last-dimension stride must be 1 / x, ckpt, work and the fused seam's buffers must be 16-byte aligned";
         case SS2D_EDEVICE: return "no sm_100 device";
         default: return code > 0 ? cudaGetErrorString(static_cast<cudaError_t>(code)) : "unknown ss2d error";
     }

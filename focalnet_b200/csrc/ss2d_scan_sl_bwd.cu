@@ -476,6 +476,7 @@ static int launch_bwd_t(const ss2d_scan_bwd_params &pb, cudaStream_t stream, Cro
     fl.vec_out = p.out && aligned16(p.out) && (p.out_bstride * eo) % 16 == 0 && (p.out_dstride * eo) % 16 == 0;
     fl.vec_dbc = aligned16(pb.dB) && aligned16(pb.dC) && p.seqlen % 4 == 0;
     fl.vec_grad = aligned16(pb.du) && aligned16(pb.ddelta) && (!pb.dz || aligned16(pb.dz)) && (p.seqlen * ei) % 16 == 0;
+    if (p.ckpt && !aligned16(p.ckpt)) return SS2D_ESTRIDE;  // read with 8/16-byte loads
     const int64_t grid = p.batch * p.ngroups * tiles;
     const bool fast = fl.vec_u && fl.vec_delta && fl.vec_bc && fl.vec_dout && fl.vec_dbc && fl.vec_grad && p.seqlen % BK == 0 && !p.z;
     auto go = [&](auto kern) -> int {

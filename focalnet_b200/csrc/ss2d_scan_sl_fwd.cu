@@ -360,6 +360,7 @@ static int launch_fwd_t(const ss2d_scan_fwd_params &p, cudaStream_t stream, Cros
     const int tiles = (per_g + SM::CPC - 1) / SM::CPC;
     Flags fl{};
     fill_flags(p, sizeof(in_t), sizeof(out_t), fl);
+    if ((p.x && !aligned16(p.x)) || (p.ckpt && !aligned16(p.ckpt))) return SS2D_ESTRIDE;  // written with 16-byte stores
     const int64_t grid = p.batch * p.ngroups * tiles;
     const bool fast = fl.vec_u && fl.vec_delta && fl.vec_bc && fl.vec_out && p.seqlen % BK == 0 && !p.z;
     auto go = [&](auto kern) -> int {

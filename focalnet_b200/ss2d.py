@@ -317,12 +317,14 @@ def cross_selective_scan(
     _chk(K == 4 and dt_low_rank, "fused SS2D core supports the 4-direction low-rank-dt configuration of the model")
     xin = x.float() if force_fp32 else x
     xf = xin.reshape(B, D, L)
-    x_dbl = torch.matmul(x_proj_weight.reshape(K * (R + 2 * N), D).to(xf.dtype), xf)  # (B, K*(R+2N), L) spatial
-    if x_proj_bias is not None:
-        x_dbl = x_dbl + x_proj_bias.reshape(1, -1, 1).to(x_dbl.dtype)
+    # the two projections stay on the reference's own library call, 1x1 conv1d (vmamba_layers.py:262-264): same cuDNN
+    # kernels and the same TF32 policy (torch.backends.cudnn.allow_tf32) as the code this replaces — x_proj un-grouped,
+    # because all four directions read the same spatial-order x
+    x_dbl = F.conv1d(xf, x_proj_weight.reshape(K * (R + 2 * N), D, 1).to(xf.dtype),
+                     None if x_proj_bias is None else x_proj_bias.reshape(-1).to(xf.dtype))  # (B, K*(R+2N), L) spatial
     x_dbl = _to_scan_order(x_dbl.view(B, K, R + 2 * N, L), H, W)
     dts_lr, Bs, Cs = torch.split(x_dbl, [R, N, N], dim=2)
-    dts = torch.matmul(dt_projs_weight.to(x_dbl.dtype).unsqueeze(0), dts_lr).reshape(B, K * D, L)  # scan order
+    dts = F.conv1d(dts_lr.reshape(B, K * R, L), dt_projs_weight.reshape(K * D, R, 1).to(x_dbl.dtype), groups=K)  # scan order
     As = -torch.exp(A_logs.to(torch.float))
     y = FusedCrossScanFn.apply(xin, dts, As, Bs, Cs, Ds.to(torch.float), dt_projs_bias.reshape(-1).to(torch.float),
                                delta_softplus)
@@ -348,10 +350,10 @@ def ss2d_forward(m: torch.nn.Module, x: torch.Tensor) -> torch.Tensor:
     N = m.A_logs.shape[1]
     K, _, R = m.dt_projs_weight.shape
     L = H * W
-    x_dbl = torch.matmul(m.x_proj_weight.reshape(K * (R + 2 * N), D), xc.reshape(B, D, L))
+    x_dbl = F.conv1d(xc.reshape(B, D, L), m.x_proj_weight.reshape(K * (R + 2 * N), D, 1))  # the reference's library call
     x_dbl = _to_scan_order(x_dbl.view(B, K, R + 2 * N, L), H, W)
     dts_lr, Bs, Cs = torch.split(x_dbl, [R, N, N], dim=2)
-    dts = torch.matmul(m.dt_projs_weight.unsqueeze(0), dts_lr).reshape(B, K * D, L)
+    dts = F.conv1d(dts_lr.reshape(B, K * R, L), m.dt_projs_weight.reshape(K * D, R, 1), groups=K)
     y = FusedCrossScanFn.apply(xc, dts, -torch.exp(m.A_logs.float()), Bs, Cs, m.Ds.float(), m.dt_projs_bias.reshape(-1).float(), True)
     y = merge_norm_gate(y, m.out_norm.weight, m.out_norm.bias, m.out_norm.eps, z=xz[..., D:]).view(B, H, W, D)
     return m.dropout(m.out_proj(y))

@@ -41,7 +41,9 @@ enum {
     SS2D_OK = 0,
     SS2D_EINVAL = -22,      /* null pointer / bad size / dim % ngroups != 0 / dstate > 256          */
     SS2D_EDTYPE = -2,       /* unsupported dtype combination (out must be F32 or == in)              */
-    SS2D_ESTRIDE = -3,      /* a last-dimension stride != 1 (selective_scan_oflex.cpp:181-182,198)   */
+    SS2D_ESTRIDE = -3,      /* a last-dimension stride != 1 (selective_scan_oflex.cpp:181-182,198), or x / ckpt /
+                               work (and, for the fused seam with `work`, y / dy / dx / ddelta / dB / dC) not
+                               16-byte aligned                                                        */
     SS2D_EDEVICE = -4       /* no sm_100 device / kernel image missing                               */
 };
 
