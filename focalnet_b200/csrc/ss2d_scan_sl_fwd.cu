@@ -314,7 +314,7 @@ sl_fwd_cross_kernel(const ss2d_scan_fwd_params p, const int tiles_per_group, con
 }
 
 bool supported(const ss2d_scan_fwd_params &p) {
-    if (p.dstate != kN || p.seqlen > 0x7fffffffLL - 4096) return false;
+    if (p.dstate != kN || p.seqlen > (1LL << 28)) return false;  // step positions and tail byte counts are 32-bit
     // SS2D_SCAN_IMPL=warpscan / statelanes pins the family (tests, A/B timing); read per call so a test can flip it
     const char *e = getenv("SS2D_SCAN_IMPL");
     if (e && e[0] == 'w') return false;
