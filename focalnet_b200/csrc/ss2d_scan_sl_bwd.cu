@@ -41,17 +41,18 @@ template <typename in_t, typename out_t, int SN, int NW> struct BwdSmem {
     static constexpr int xch_off = NSTAGE * stage_bytes;            // [warp][buf][dl|du|go][q][cw] float4
     static constexpr int XBUF = 3 * NQ * M::CPW;                    // float4 per buffer
     static constexpr int xch_warp = 2 * XBUF * 16;
-    static constexpr int red_off = xch_off + NW * xch_warp;        // [warp][(dB|dC, s, q)][lane] float4
+    static constexpr int red_off = xch_off + NW * xch_warp;        // [buf][warp][q][lane] float4: dB/dC summed over the warp's channels
     static constexpr int NIDX = 2 * SN * NQ;
-    static constexpr int red_warp = NIDX * kWarp * 16;
-    static constexpr int total = red_off + NW * red_warp;
+    static constexpr int red_warp = NQ * kWarp * 16;
+    static constexpr int red_buf = NW * red_warp;
+    static constexpr int total = red_off + 2 * red_buf;
     static_assert(NIDX * M::LPC == 128, "one reduction output per (which, state, q)");
+    static_assert(2 * SN == M::CPW, "the lane reduction over a warp's channels leaves one (which, state) per channel slot");
 };
 
 // Iteration k of the block loop (k = nblk-1 .. 0), software pipelined by hand:
 //   [ sum + red.global of block k+1's staged dB/dC | du, ddelta of block k+1 | softplus of block k-1 | F(k) ]
-//   barrier  (everyone is done reading the staging area)
-//   [ R(k): dx chain, gradient products, staging of dB/dC ]
+//   [ R(k): dx chain, gradient products; dB/dC summed over the warp's channels by shuffles, staged (double buffered) ]
 //   barrier  (staging complete; the tile of block k-1 has landed)
 // CROSS (fused seam S3, FAST only): u and dout are read from the fp32 planes x[b,d] / dy[b,d] (directions 0 / 2,
 // forwards / backwards) or from their transposed copies aux.uT / aux.doutT (directions 1 / 3); du is accumulated
@@ -87,8 +88,9 @@ sl_bwd_kernel(const ss2d_scan_bwd_params pb, const int tiles_per_group, const Fl
     // element (kind, step j, channel) of buffer f lives at float index (((f*3 + kind)*NQ + j/4)*CPW + cw)*4 + j%4
     float *xpub = xch + (((OWN * ng) >> 2) * CPW + cw) * 4 + ((OWN * ng) & 3);
     const float4 *xq = reinterpret_cast<const float4 *>(xch) + cw;
-    float4 *red_w = reinterpret_cast<float4 *>(smem + SM::red_off + warp * SM::red_warp) + lane;
+    float4 *red_w = reinterpret_cast<float4 *>(smem + SM::red_off + warp * SM::red_warp) + lane;  // + q*32 (+ buffer)
     const float4 *red_all = reinterpret_cast<const float4 *>(smem + SM::red_off);
+    constexpr int RBUF = SM::red_buf / 16;  // float4 per staging buffer
 
     const int64_t row0 = (int64_t)g * per_g + ch0;
     const int64_t urow0 = CROSS ? ch0 : row0;  // row of u / dout / du: d in fused mode
@@ -176,9 +178,8 @@ sl_bwd_kernel(const ss2d_scan_bwd_params pb, const int tiles_per_group, const Fl
         const int o = i * NT + threadIdx.x;
         const int idx = o / LPC, ngo = o % LPC;
         const int which = idx / (SN * NQ), s = (idx / NQ) % SN, q = idx % NQ;
-        // SN == 4: two idx share one LDS.128 phase — the odd one visits the channels in swapped-pair order (xor 1),
-        // so the phase's 8 lanes hit distinct banks
-        red_src[i] = idx * kWarp + ngo + (SN == 4 ? (idx & 1) * LPC : 0);
+        // after the lane reduction the sum of (which, s) over a warp's channels sits in channel slot which*SN + s
+        red_src[i] = q * kWarp + (which * SN + s) * LPC + ngo;
         red_q[i] = q;
         red_dst[i] = (which ? pb.dC : pb.dB) + (((int64_t)b * p.ngroups + g) * kN + ngo * SN + s) * (int64_t)L + 4 * q;
     }
@@ -258,18 +259,15 @@ sl_bwd_kernel(const ss2d_scan_bwd_params pb, const int tiles_per_group, const Fl
     // dB / dC of a finished block: sum the staged products over the CTA's channels, one vector reduction per (state, 4 steps)
 #pragma unroll
     for (int i = 0; i < OPT; ++i) red_dst[i] += (int64_t)nblk * BK;  // one block right of the last: walks left per call
-    auto reduce_bc = [&](int k) {
+    auto reduce_bc = [&](int k, int buf) {
 #pragma unroll
         for (int i = 0; i < OPT; ++i) {
             float2 lo = make_float2(0.f, 0.f), hi = make_float2(0.f, 0.f);
 #pragma unroll
             for (int w = 0; w < NW; ++w) {
-#pragma unroll
-                for (int kk = 0; kk < CPW; ++kk) {
-                    const float4 v = red_all[w * (NIDX * kWarp) + (SN == 4 ? (red_src[i] ^ (kk * LPC)) : red_src[i] + kk * LPC)];
-                    lo = __fadd2_rn(lo, make_float2(v.x, v.y));
-                    hi = __fadd2_rn(hi, make_float2(v.z, v.w));
-                }
+                const float4 v = red_all[buf + w * (NQ * kWarp) + red_src[i]];
+                lo = __fadd2_rn(lo, make_float2(v.x, v.y));
+                hi = __fadd2_rn(hi, make_float2(v.z, v.w));
             }
             red_dst[i] -= BK;
             float *dst = red_dst[i];
@@ -329,6 +327,7 @@ sl_bwd_kernel(const ss2d_scan_bwd_params pb, const int tiles_per_group, const Fl
     int slot0 = ((nblk - 1) % NSTAGE) * SM::stage_bytes;  // ring slots of blocks k, k-1, k-2 (byte offsets), rotated per iteration
     int slot1 = ((nblk + 1) % NSTAGE) * SM::stage_bytes;  // (k-1) mod 3 == (k+2) mod 3
     int slot2 = (nblk % NSTAGE) * SM::stage_bytes;        // (k-2) mod 3 == (k+1) mod 3
+    int rcur = 0;                                         // staging buffer (float4 index) block k writes; block k+1 wrote the other
     int xcur = ((nblk - 1) & 1) * XBUF;                   // exchange buffer (float4 index) of block k; block k-1 uses the other
     issue(nblk - 1, slot0);
     issue(nblk - 2, slot1);
@@ -349,7 +348,7 @@ sl_bwd_kernel(const ss2d_scan_bwd_params pb, const int tiles_per_group, const Fl
         issue(k - 2, slot2);  // ring slot of block k+1, free since the barrier that ended iteration k+1
         const float4 hin_next = load_ck(k >= 2);
         // ---- block k+1: dB/dC sums, du / ddelta (first iteration: all-zero dummies, nothing stored) ----
-        if (k + 1 < nblk) reduce_bc(k + 1);
+        if (k + 1 < nblk) reduce_bc(k + 1, rcur ^ RBUF);
         finalize(k + 1, sacc, wacc, uv_p, dl_p, gv_p, active && k + 1 < nblk);
         // ---- block k-1: softplus of this lane's own steps ----
         float uv_n[OWN], dl_n[OWN], gv_n[OWN];
@@ -386,8 +385,7 @@ sl_bwd_kernel(const ss2d_scan_bwd_params pb, const int tiles_per_group, const Fl
                 H2[s][2 * q] = h0; H2[s][2 * q + 1] = h1;
             }
         }
-        __syncthreads();  // every thread is done reading block k+1's staged dB / dC products
-        // ---- R(k): walk the block right to left ----
+        // ---- R(k): walk the block right to left (stages into the buffer block k+1 did not use: no barrier needed here) ----
 #pragma unroll
         for (int j = 0; j < BK / 2; ++j) { sacc[j] = make_float2(0.f, 0.f); wacc[j] = make_float2(0.f, 0.f); }
 #pragma unroll
@@ -397,6 +395,7 @@ sl_bwd_kernel(const ss2d_scan_bwd_params pb, const int tiles_per_group, const Fl
             const float2 du0 = make_float2(duq.x, duq.y), du1 = make_float2(duq.z, duq.w);
             const float2 nu0 = make_float2(-duq.x, -duq.y), nu1 = make_float2(-duq.z, -duq.w);
             const float2 go0 = make_float2(goq.x, goq.y), go1 = make_float2(goq.z, goq.w);
+            float4 V[CPW];  // this lane's dB (slots 0..SN-1) and dC (slots SN..2SN-1) products of the 4 steps
 #pragma unroll
             for (int s = 0; s < SN; ++s) {
                 float Bv[4], Cv[4];
@@ -424,9 +423,24 @@ sl_bwd_kernel(const ss2d_scan_bwd_params pb, const int tiles_per_group, const Fl
                 wacc[2 * q + 1] = __ffma2_rn(pq1, And, wacc[2 * q + 1]);
                 dA2[s] = __ffma2_rn(pq0, dl0, dA2[s]);
                 dA2[s] = __ffma2_rn(pq1, dl1, dA2[s]);
-                red_w[(s * NQ + q) * kWarp] = make_float4(dB0.x, dB0.y, dB1.x, dB1.y);
-                red_w[((SN + s) * NQ + q) * kWarp] = make_float4(dC0.x, dC0.y, dC1.x, dC1.y);
+                V[s] = make_float4(dB0.x, dB0.y, dB1.x, dB1.y);
+                V[SN + s] = make_float4(dC0.x, dC0.y, dC1.x, dC1.y);
             }
+            // sum over the warp's CPW channels: transposed reduction across the channel bits of the lane id — CPW float4
+            // in, ONE out (slot == this lane's channel index), CPW-1 float4 exchanged instead of CPW-1 staged and re-read
+#pragma unroll
+            for (int m = CPW / 2; m >= 1; m >>= 1) {
+                const bool up = (cw & m) != 0;
+#pragma unroll
+                for (int j = 0; j < m; ++j) {
+                    const float4 snd = up ? V[j] : V[j + m], kp = up ? V[j + m] : V[j];
+                    V[j].x = kp.x + __shfl_xor_sync(0xffffffffu, snd.x, m * LPC);
+                    V[j].y = kp.y + __shfl_xor_sync(0xffffffffu, snd.y, m * LPC);
+                    V[j].z = kp.z + __shfl_xor_sync(0xffffffffu, snd.z, m * LPC);
+                    V[j].w = kp.w + __shfl_xor_sync(0xffffffffu, snd.w, m * LPC);
+                }
+            }
+            red_w[rcur + q * kWarp] = V[0];
         }
 #pragma unroll
         for (int i = 0; i < OWN; ++i) {
@@ -436,10 +450,11 @@ sl_bwd_kernel(const ss2d_scan_bwd_params pb, const int tiles_per_group, const Fl
         hin = hin_next;
         { const int t = slot0; slot0 = slot1; slot1 = slot2; slot2 = t; }
         xcur ^= XBUF;
+        rcur ^= RBUF;
         cp_async_wait<0>();  // the tile of block k-2 (issued at the top) has landed for this thread ...
         __syncthreads();     // ... and for everyone; block k's staged dB / dC products are complete
     }
-    reduce_bc(0);
+    reduce_bc(0, rcur ^ RBUF);
     finalize(0, sacc, wacc, uv_p, dl_p, gv_p, active);
 
     // ---- per-channel sums over time (atomically over batch) ----
