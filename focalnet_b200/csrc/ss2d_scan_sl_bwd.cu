@@ -11,10 +11,11 @@
 // blocks of 16 steps.  Per block: (F) recompute a_t, h_t of the 16 steps from the forward's checkpoint at the
 // block's left edge, keeping them in registers; (R) walk the block backwards — the dx recurrence is a serial
 // FFMA chain, everything else is evaluated on step PAIRS with FMUL2 / FFMA2.  One ex2 per (element, state) in the
-// whole backward; no warp scan.  The per-channel dB / dC products are staged in shared memory lane-contiguously
-// and summed over ALL channels of the CTA (two block barriers per 16 steps) before ONE red.global.add.v4.f32 per
-// (state, 4 steps) leaves the CTA (the reference issues one scalar atomic per channel per element).  Sums over the
-// 16 states (du, ddelta) are transposed reductions over the channel's lanes.
+// whole backward; no warp scan.  The per-channel dB / dC products are summed over the warp's channels by a transposed
+// shuffle reduction, the warp sums are staged in shared memory (double buffered, one block barrier per 16 steps) and
+// summed over the CTA's warps before ONE red.global.add.v4.f32 per (state, 4 steps) leaves the CTA (the reference
+// issues one scalar atomic per channel per element).  Sums over the 16 states (du, ddelta) are transposed reductions
+// over the channel's lanes.
 #include "ss2d_scan_sl.cuh"
 #include <cstdlib>
 
@@ -395,7 +396,7 @@ sl_bwd_kernel(const ss2d_scan_bwd_params pb, const int tiles_per_group, const Fl
             const float2 du0 = make_float2(duq.x, duq.y), du1 = make_float2(duq.z, duq.w);
             const float2 nu0 = make_float2(-duq.x, -duq.y), nu1 = make_float2(-duq.z, -duq.w);
             const float2 go0 = make_float2(goq.x, goq.y), go1 = make_float2(goq.z, goq.w);
-            float4 V[CPW];  // this lane's dB (slots 0..SN-1) and dC (slots SN..2SN-1) products of the 4 steps
+            float V[CPW][4];  // this lane's dB (slots 0..SN-1) and dC (slots SN..2SN-1) products of the 4 steps
 #pragma unroll
             for (int s = 0; s < SN; ++s) {
                 float Bv[4], Cv[4];
@@ -423,8 +424,8 @@ sl_bwd_kernel(const ss2d_scan_bwd_params pb, const int tiles_per_group, const Fl
                 wacc[2 * q + 1] = __ffma2_rn(pq1, And, wacc[2 * q + 1]);
                 dA2[s] = __ffma2_rn(pq0, dl0, dA2[s]);
                 dA2[s] = __ffma2_rn(pq1, dl1, dA2[s]);
-                V[s] = make_float4(dB0.x, dB0.y, dB1.x, dB1.y);
-                V[SN + s] = make_float4(dC0.x, dC0.y, dC1.x, dC1.y);
+                V[s][0] = dB0.x; V[s][1] = dB0.y; V[s][2] = dB1.x; V[s][3] = dB1.y;
+                V[SN + s][0] = dC0.x; V[SN + s][1] = dC0.y; V[SN + s][2] = dC1.x; V[SN + s][3] = dC1.y;
             }
             // sum over the warp's CPW channels: transposed reduction across the channel bits of the lane id — CPW float4
             // in, ONE out (slot == this lane's channel index), CPW-1 float4 exchanged instead of CPW-1 staged and re-read
@@ -433,14 +434,15 @@ sl_bwd_kernel(const ss2d_scan_bwd_params pb, const int tiles_per_group, const Fl
                 const bool up = (cw & m) != 0;
 #pragma unroll
                 for (int j = 0; j < m; ++j) {
-                    const float4 snd = up ? V[j] : V[j + m], kp = up ? V[j + m] : V[j];
-                    V[j].x = kp.x + __shfl_xor_sync(0xffffffffu, snd.x, m * LPC);
-                    V[j].y = kp.y + __shfl_xor_sync(0xffffffffu, snd.y, m * LPC);
-                    V[j].z = kp.z + __shfl_xor_sync(0xffffffffu, snd.z, m * LPC);
-                    V[j].w = kp.w + __shfl_xor_sync(0xffffffffu, snd.w, m * LPC);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const float snd = up ? V[j][e] : V[j + m][e];
+                        const float kp = up ? V[j + m][e] : V[j][e];
+                        V[j][e] = kp + __shfl_xor_sync(0xffffffffu, snd, m * LPC);
+                    }
                 }
             }
-            red_w[rcur + q * kWarp] = V[0];
+            red_w[rcur + q * kWarp] = make_float4(V[0][0], V[0][1], V[0][2], V[0][3]);
         }
 #pragma unroll
         for (int i = 0; i < OWN; ++i) {

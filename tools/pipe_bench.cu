@@ -137,6 +137,28 @@ __global__ void k_red4(float *buf, size_t n4, int reps) {
     }
 }
 
+// LDS.128 and SHFL interleaved (ILP LDS.128 + 4*ILP SHFL per iteration): do shuffles share the shared-memory data pipe?
+__global__ void k_lds_shfl(float *out, float seed) {
+    __shared__ float4 sm[1024];
+    for (int i = threadIdx.x; i < 1024; i += blockDim.x) sm[i] = make_float4(seed, seed, seed, seed);
+    __syncthreads();
+    float4 acc = make_float4(0, 0, 0, 0);
+    float v[4 * ILP];
+#pragma unroll
+    for (int i = 0; i < 4 * ILP; ++i) v[i] = seed + i + threadIdx.x;
+    int idx = threadIdx.x;
+    for (int it = 0; it < ITERS; ++it) {
+#pragma unroll
+        for (int i = 0; i < ILP; ++i) {
+            float4 t = sm[(idx + i * 32) & 1023]; acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) v[4 * i + j] = __shfl_up_sync(0xffffffffu, v[4 * i + j], 1);
+        }
+        idx += 1;
+    }
+    float s = acc.x + acc.y + acc.z + acc.w; for (int i = 0; i < 4 * ILP; ++i) s += v[i];
+    if (s == 123.456f) out[0] = s;
+}
 template <typename F> float time_ms(F f, int n = 5) {
     cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
     f(); cudaDeviceSynchronize();
@@ -169,6 +191,7 @@ int main() {
     rep("mix FFMA2+FFMA+MUFU (total)", time_ms([&] { k_mix2<<<blocks, threads>>>(out, 0.5f); }), 3);
     rep("SHFL.UP", time_ms([&] { k_shfl<<<blocks, threads>>>(out, 0.5f); }), 1);
     rep("LDS.128 (conflict-free)", time_ms([&] { k_lds128<<<blocks, threads>>>(out, 0.5f); }), 1);
+    rep("1 LDS.128 + 4 SHFL (total)", time_ms([&] { k_lds_shfl<<<blocks, threads>>>(out, 0.5f); }), 5);
     // reductions: 64 MB window (fits L2), 16 M threads x reps
     size_t n = 16u << 20; float *buf; CK(cudaMalloc(&buf, n * 4)); CK(cudaMemset(buf, 0, n * 4));
     for (int reps : {1, 8}) {
