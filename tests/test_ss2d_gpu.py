@@ -293,3 +293,20 @@ def test_cross_permute_is_per_direction_scan_order_and_invertible(shape):
     out.backward(g)
     back = ToScanOrderFn.apply(t.grad, H, W)       # permuting the gradient again must give g back (inverse map)
     assert torch.equal(back, g)
+
+
+@pytest.mark.parametrize("shape", [(3, 64, 64), (2, 30, 41), (5, 1, 7)])
+def test_plane_transpose_and_accumulate(shape):
+    """ss2d_plane_transpose: dst = src^T and dst += src^T (the fused seam's x^T / y^T plumbing) — bit-exact data movement."""
+    from focalnet_b200 import _lib
+    P, H, W = shape
+    g = torch.Generator().manual_seed(7)
+    src = torch.randn(P, H, W, generator=g).cuda()
+    dst = torch.empty(P, W, H, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    _lib.check(_lib.lib().ss2d_plane_transpose(src.data_ptr(), dst.data_ptr(), P, H, W, 0, st), "ss2d_plane_transpose")
+    assert torch.equal(dst, src.transpose(1, 2))
+    acc = torch.randn(P, W, H, generator=g).cuda()
+    ref = acc + src.transpose(1, 2)
+    _lib.check(_lib.lib().ss2d_plane_transpose(src.data_ptr(), acc.data_ptr(), P, H, W, 1, st), "ss2d_plane_transpose")
+    assert torch.equal(acc, ref)
