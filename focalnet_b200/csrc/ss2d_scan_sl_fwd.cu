@@ -303,7 +303,7 @@ __device__ __forceinline__ void sl_fwd_body(const ss2d_scan_fwd_params &p, const
 // two entry points over one body: the fused variant carries the gather state and is capped at 168 registers (3 CTAs per
 // SM); the plain one is left to ptxas (137 registers) — an explicit minimum-blocks bound makes it spend all it is given
 template <typename in_t, typename out_t, int SN, int NW, int TT, bool FAST>
-__global__ void __launch_bounds__(NW *kWarp)
+__global__ void __launch_bounds__(NW *kWarp, sizeof(in_t) == 2 ? 3 : 0)  // 16-bit inputs: cap at 168 registers (3 CTAs/SM)
 sl_fwd_kernel(const ss2d_scan_fwd_params p, const int tiles_per_group, const Flags fl) {
     sl_fwd_body<in_t, out_t, SN, NW, TT, FAST, false>(p, tiles_per_group, fl, CrossAux{nullptr, nullptr, nullptr});
 }
