@@ -12,6 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libss2d_b200.so")
 
 F32, F16, BF16 = 0, 1, 2
+FAMILY_AUTO, FAMILY_STATELANES, FAMILY_WARPSCAN = 0, 1, 2
 REF_CHUNK = 2048
 SL_BLOCK = 16  # sequences up to this length need no checkpoints at all
 
@@ -21,7 +22,7 @@ _vp, _i64, _i32 = C.c_void_p, C.c_int64, C.c_int32
 class ScanFwdParams(C.Structure):
     _fields_ = (
         [(n, _i64) for n in ("batch", "dim", "seqlen", "dstate", "ngroups")]
-        + [(n, _i32) for n in ("in_dtype", "out_dtype", "delta_softplus", "reserved0")]
+        + [(n, _i32) for n in ("in_dtype", "out_dtype", "delta_softplus", "family")]
         + [(n, _vp) for n in ("u", "delta", "A", "B", "C", "D", "delta_bias", "z")]
         + [(n, _i64) for n in ("u_bstride", "u_dstride", "delta_bstride", "delta_dstride", "B_bstride", "B_gstride",
                                 "B_nstride", "C_bstride", "C_gstride", "C_nstride", "z_bstride", "z_dstride")]
@@ -39,7 +40,7 @@ class ScanBwdParams(C.Structure):
 class CrossFwdParams(C.Structure):
     _fields_ = (
         [(n, _i64) for n in ("batch", "D", "H", "W", "dstate")]
-        + [("in_dtype", _i32), ("delta_softplus", _i32)]
+        + [("in_dtype", _i32), ("delta_softplus", _i32), ("family", _i32), ("deterministic", _i32)]
         + [(n, _vp) for n in ("x", "delta", "B", "C", "A", "Dskip", "delta_bias", "y", "ckpt")]
         + [("bc_bstride", _i64), ("bc_gstride", _i64), ("work", _vp)]
     )
@@ -51,6 +52,7 @@ class CrossBwdParams(C.Structure):
 
 
 EXPORTS = ("ss2d_abi_version", "ss2d_build_info", "ss2d_error_string", "ss2d_scan_ckpt_floats", "ss2d_cross_work_floats",
+           "ss2d_scan_family", "ss2d_set_default_family", "ss2d_cross_family",
            "ss2d_plane_transpose", "ss2d_selective_scan_fwd",
            "ss2d_selective_scan_bwd", "ss2d_cross_scan", "ss2d_cross_merge", "ss2d_cross_scan_fwd",
            "ss2d_cross_scan_bwd", "ss2d_dwconv_silu_fwd", "ss2d_dwconv_silu_bwd", "ss2d_merge_norm_gate_fwd",
@@ -75,7 +77,13 @@ def lib():
         L.ss2d_scan_ckpt_floats.restype = _i64
         L.ss2d_scan_ckpt_floats.argtypes = [_i64, _i64, _i64, _i64]
         L.ss2d_cross_work_floats.restype = _i64
-        L.ss2d_cross_work_floats.argtypes = [_i64, _i64, _i64, _i64, _i64, _i32, _i32]
+        L.ss2d_cross_work_floats.argtypes = [_i64, _i64, _i64, _i64, _i64, _i32, _i32, _i32]
+        L.ss2d_scan_family.restype = C.c_int
+        L.ss2d_scan_family.argtypes = [_vp]
+        L.ss2d_set_default_family.restype = C.c_int
+        L.ss2d_set_default_family.argtypes = [C.c_int]
+        L.ss2d_cross_family.restype = C.c_int
+        L.ss2d_cross_family.argtypes = [_i64, _i64, _i64, _i64, _i64, _i32, _i32]
         sigs = {n: [_vp, _vp] for n in ("ss2d_selective_scan_fwd", "ss2d_selective_scan_bwd", "ss2d_cross_scan_fwd",
                                         "ss2d_cross_scan_bwd")}
         sigs.update({n: [_vp, _vp, _i64, _i64, _i64, _i64, _i32, _vp] for n in ("ss2d_cross_scan", "ss2d_cross_merge")})
@@ -90,7 +98,7 @@ def lib():
             fn = getattr(L, name)  # AttributeError here == a symbol of include/ss2d_b200.h is not exported
             fn.restype = C.c_int
             fn.argtypes = argtypes
-        if L.ss2d_abi_version() != 2:
+        if L.ss2d_abi_version() != 3:
             raise RuntimeError("libss2d_b200.so ABI version mismatch")
         _lib = L
     return _lib

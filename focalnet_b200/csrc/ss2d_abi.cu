@@ -8,7 +8,7 @@
 extern "C" int ss2d_abi_version(void) { return SS2D_ABI_VERSION; }
 
 extern "C" const char *ss2d_build_info(void) {
-    return "libss2d_b200 abi=2 arch=sm_100a kernels=scan_sl_fwd,scan_sl_bwd,scan_fwd,scan_bwd,cross_scan,cross_merge,cross_scan_fused,dwconv_silu,merge_norm_gate "
+    return "libss2d_b200 abi=3 arch=sm_100a kernels=scan_sl_fwd,scan_sl_bwd,scan_fwd,scan_bwd,cross_scan,cross_merge,cross_scan_fused,dwconv_silu,merge_norm_gate "
            "cuda=" SS2D_STR(__CUDACC_VER_MAJOR__) "." SS2D_STR(__CUDACC_VER_MINOR__);
 }
 
@@ -19,12 +19,28 @@ extern "C" int64_t ss2d_scan_ckpt_floats(int64_t batch, int64_t dim, int64_t seq
     return fine > coarse ? fine : coarse;  // one size serves whichever kernel family takes the shape
 }
 
-extern "C" int64_t ss2d_cross_work_floats(int64_t batch, int64_t D, int64_t H, int64_t W, int64_t dstate, int32_t in_dtype,
-                                          int32_t backward) {
-    if (batch <= 0 || D <= 0 || H <= 0 || W <= 0 || in_dtype != SS2D_F32 || (H * W) % SS2D_SL_BLOCK != 0) return 0;
+extern "C" int ss2d_scan_family(const ss2d_scan_fwd_params *p) {
+    if (!p) return SS2D_EINVAL;
+    return ss2d::sl::supported(*p) ? SS2D_FAMILY_STATELANES : SS2D_FAMILY_WARPSCAN;
+}
+
+extern "C" int ss2d_set_default_family(int family) { return ss2d::sl::set_default_family(family); }
+
+// the fused seam runs on the state-lanes kernels for fp32 / dstate 16 / L % 16 == 0 problems that `supported` takes
+static bool cross_on_statelanes(int64_t batch, int64_t D, int64_t H, int64_t W, int64_t dstate, int32_t in_dtype, int32_t family) {
+    if (batch <= 0 || D <= 0 || H <= 0 || W <= 0 || in_dtype != SS2D_F32 || (H * W) % SS2D_SL_BLOCK != 0) return false;
     ss2d_scan_fwd_params p{};
-    p.batch = batch; p.dim = 4 * D; p.seqlen = H * W; p.dstate = dstate; p.ngroups = 4;
-    if (!ss2d::sl::supported(p)) return 0;
+    p.batch = batch; p.dim = 4 * D; p.seqlen = H * W; p.dstate = dstate; p.ngroups = 4; p.family = family;
+    return ss2d::sl::supported(p);
+}
+
+extern "C" int ss2d_cross_family(int64_t batch, int64_t D, int64_t H, int64_t W, int64_t dstate, int32_t in_dtype, int32_t family) {
+    return cross_on_statelanes(batch, D, H, W, dstate, in_dtype, family) ? SS2D_FAMILY_STATELANES : SS2D_FAMILY_WARPSCAN;
+}
+
+extern "C" int64_t ss2d_cross_work_floats(int64_t batch, int64_t D, int64_t H, int64_t W, int64_t dstate, int32_t in_dtype,
+                                          int32_t backward, int32_t family) {
+    if (!cross_on_statelanes(batch, D, H, W, dstate, in_dtype, family)) return 0;
     return (backward ? 3 : 2) * batch * D * H * W;
 }
 

@@ -136,7 +136,13 @@ __device__ __forceinline__ void store_block(T *__restrict__ p, const float (&v)[
 // warp-wide scalar access still touches whole 32-byte sectors (4 rows x 8 pixels for H=64, T=16).
 struct CrossInfo {
     int H, W;
+    int g_only;  // < 0: the grid covers all groups; else one launch serves direction g_only alone (deterministic merge order)
 };
+// (group, batch) of a CTA: blockIdx.x / tiles_per_group enumerates (batch, group) pairs, or batches when one group is pinned
+__device__ __forceinline__ void cta_group_batch(const CrossInfo &ci, int bg, int ngroups, int &g, int &b) {
+    if (ci.g_only >= 0) { g = ci.g_only; b = bg; }
+    else { g = bg % ngroups; b = bg / ngroups; }
+}
 struct CrossWalk {  // pixel offset of scan step l for k in {1,3}, advanced one step at a time
     int h, w, W, H, dir;
     __device__ __forceinline__ CrossWalk(int k, int64_t l, int64_t L, int H_, int W_) : W(W_), H(H_) {
@@ -363,4 +369,21 @@ __device__ __forceinline__ void shift_down1(float P, float H, float &Pe, float &
         : "f"(H), "f"(P));
 }
 
+// Dynamic shared memory opt-in, raised at most once per (kernel instantiation, device, size): cudaFuncSetAttribute is a
+// driver round trip that has no business on every launch.  One static per instantiation of this template == per kernel.
+template <typename K> static inline int smem_optin(K kern, int bytes) {
+    static int done_dev = -1, done_bytes = 0;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return (int)e;
+    if (done_dev != dev || bytes > done_bytes) {
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+        if (e != cudaSuccess) return (int)e;
+        done_dev = dev;
+        done_bytes = bytes;
+    }
+    return 0;
+}
+
 }  // namespace ss2d
+

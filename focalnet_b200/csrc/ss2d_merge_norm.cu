@@ -195,8 +195,8 @@ extern "C" int ss2d_merge_norm_gate_fwd(const float *y, const float *weight, con
     if (tiles * batch > 0x7fffffffLL) return SS2D_EINVAL;
     const size_t smem = mn_smem((int)D);
     auto go = [&](auto kern) -> int {
-        cudaError_t e2 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e2 != cudaSuccess) return (int)e2;
+        const int rc = smem_optin(kern, (int)smem);
+        if (rc != 0) return rc;
         kern<<<(unsigned)(tiles * batch), kMnWarps * kWarp, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
             y, weight, bias, z, z_pstride, out, (int)D, L, eps, (int)tiles);
         return (int)cudaGetLastError();
@@ -224,8 +224,8 @@ extern "C" int ss2d_merge_norm_gate_bwd(const float *y, const float *weight, con
     if (blocks > 0x7fffffffLL) return SS2D_EINVAL;
     const size_t smem = mn_smem((int)D);
     auto go = [&](auto kern) -> int {
-        cudaError_t e2 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e2 != cudaSuccess) return (int)e2;
+        const int rc = smem_optin(kern, (int)smem);
+        if (rc != 0) return rc;
         kern<<<(unsigned)blocks, kMnWarps * kWarp, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
             y, weight, bias, z, z_pstride, dout, dy, dz, dz_pstride, dweight, dbias, (int)D, L, eps, (int)tiles, tpb, (int)batch);
         return (int)cudaGetLastError();

@@ -181,7 +181,8 @@ scan_bwd_kernel(const ss2d_scan_bwd_params pb, const int tiles_per_group, const 
     const int per_g = (int)(p.dim / p.ngroups);
     const int tile = blockIdx.x % tiles_per_group;
     const int bg = blockIdx.x / tiles_per_group;
-    const int g = bg % (int)p.ngroups, b = bg / (int)p.ngroups;
+    int g, b;
+    cta_group_batch(xinfo, bg, (int)p.ngroups, g, b);
     const int c_local = tile * NW + warp;
     const bool active = c_local < per_g;
     const int64_t c = (int64_t)g * per_g + (active ? c_local : per_g - 1);
@@ -367,7 +368,7 @@ scan_bwd_kernel(const ss2d_scan_bwd_params pb, const int tiles_per_group, const 
 static inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 template <typename in_t, typename out_t, int T, int NW, int MINB, bool CROSS = false, int SB = 8>
-static int launch_bwd(const ss2d_scan_bwd_params &pb, cudaStream_t stream, CrossInfo xinfo = CrossInfo{0, 0}) {
+static int launch_bwd(const ss2d_scan_bwd_params &pb, cudaStream_t stream, CrossInfo xinfo = CrossInfo{0, 0, -1}) {
     using FT = BCTile<in_t, T, SB>;
     const ss2d_scan_fwd_params &p = pb.f;
     const int per_g = (int)(p.dim / p.ngroups);
@@ -391,10 +392,10 @@ static int launch_bwd(const ss2d_scan_bwd_params &pb, cudaStream_t stream, Cross
     // du / ddelta / dz rows are contiguous (batch, dim, L)
     fl.vec_grad = aligned16(pb.du) && aligned16(pb.ddelta) && (!pb.dz || aligned16(pb.dz)) && (p.seqlen * ei) % 16 == 0;
     if (CROSS) fl.vec_dbc = fl.vec_dbc && aligned16(pb.du);  // dx plane rows are L floats: 16-byte aligned iff L % 4 == 0
-    const int64_t grid = p.batch * p.ngroups * tiles;
+    const int64_t grid = p.batch * (xinfo.g_only >= 0 ? 1 : p.ngroups) * tiles;
     auto go = [&](auto kern) -> int {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return (int)e;
+        const int rc = smem_optin(kern, (int)smem);
+        if (rc != 0) return rc;
         kern<<<(unsigned)grid, NW * kWarp, smem, stream>>>(pb, tiles, fl, xinfo);
         return (int)cudaGetLastError();
     };
@@ -455,7 +456,7 @@ extern "C" int ss2d_cross_scan_bwd(const ss2d_cross_bwd_params *pp, void *stream
     ss2d_scan_bwd_params pb{};
     ss2d_scan_fwd_params &p = pb.f;
     p.batch = c.batch; p.dim = 4 * c.D; p.seqlen = L; p.dstate = c.dstate; p.ngroups = 4;
-    p.in_dtype = c.in_dtype; p.out_dtype = SS2D_F32; p.delta_softplus = c.delta_softplus;
+    p.in_dtype = c.in_dtype; p.out_dtype = SS2D_F32; p.delta_softplus = c.delta_softplus; p.family = c.family;
     p.u = c.x; p.delta = c.delta; p.A = c.A; p.B = c.B; p.C = c.C; p.D = c.Dskip; p.delta_bias = c.delta_bias;
     p.u_bstride = c.D * L; p.u_dstride = L;
     p.delta_bstride = 4 * c.D * L; p.delta_dstride = L;
@@ -468,7 +469,7 @@ extern "C" int ss2d_cross_scan_bwd(const ss2d_cross_bwd_params *pp, void *stream
     pb.dA = pp->dA; pb.dB = pp->dB; pb.dC = pp->dC; pb.dD = pp->dDskip; pb.ddelta_bias = pp->ddelta_bias;
     using namespace ss2d;
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-    const CrossInfo xi{(int)c.H, (int)c.W};
+    const bool det = c.deterministic != 0;
     {
         ss2d_scan_fwd_params q = p;  // the forward's view of the problem decides the kernel family (checkpoint layout)
         q.out_bstride = c.D * L; q.out_dstride = L;
@@ -488,10 +489,18 @@ extern "C" int ss2d_cross_scan_bwd(const ss2d_cross_bwd_params *pp, void *stream
     }
     if (!p.ckpt && L > SS2D_CKPT_STEPS) return SS2D_EINVAL;  // the fused backward needs the forward's checkpoints
     constexpr int T = SS2D_BWD_T, NW = SS2D_BWD_NW, MINB = SS2D_BWD_MINB;
-    switch (c.in_dtype) {
-        case SS2D_F32: return launch_bwd<float, float, T, NW, MINB, true>(pb, s, xi);
-        case SS2D_F16: return launch_bwd<__half, float, T, NW, MINB, true>(pb, s, xi);
-        case SS2D_BF16: return launch_bwd<__nv_bfloat16, float, T, NW, MINB, true>(pb, s, xi);
-        default: return SS2D_EDTYPE;
+    // deterministic: dx receives the four directions in the order k = 0..3 (dA / dB / dC / dD / dbias stay sums of
+    // atomics over the channel tiles, like the reference's backward, selective_scan_bwd_kernel_oflex.cuh:259-273)
+    for (int k = det ? 0 : -1; k < (det ? 4 : 0); ++k) {
+        const CrossInfo xi{(int)c.H, (int)c.W, k};
+        int rc;
+        switch (c.in_dtype) {
+            case SS2D_F32: rc = launch_bwd<float, float, T, NW, MINB, true>(pb, s, xi); break;
+            case SS2D_F16: rc = launch_bwd<__half, float, T, NW, MINB, true>(pb, s, xi); break;
+            case SS2D_BF16: rc = launch_bwd<__nv_bfloat16, float, T, NW, MINB, true>(pb, s, xi); break;
+            default: return SS2D_EDTYPE;
+        }
+        if (rc != 0) return rc;
     }
+    return 0;
 }

@@ -98,7 +98,8 @@ scan_fwd_kernel(const ss2d_scan_fwd_params p, const int tiles_per_group, const F
     const int per_g = (int)(p.dim / p.ngroups);
     const int tile = blockIdx.x % tiles_per_group;
     const int bg = blockIdx.x / tiles_per_group;
-    const int g = bg % (int)p.ngroups, b = bg / (int)p.ngroups;
+    int g, b;
+    cta_group_batch(xinfo, bg, (int)p.ngroups, g, b);
     const int c_local = tile * NW + warp;
     const bool active = c_local < per_g;
     const int64_t c = (int64_t)g * per_g + (active ? c_local : per_g - 1);
@@ -219,7 +220,7 @@ scan_fwd_kernel(const ss2d_scan_fwd_params p, const int tiles_per_group, const F
 static inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 template <typename in_t, typename out_t, bool CROSS, int T = 16, int NW = 8, int MINB = 2, int SB = 8>
-static int launch_fwd(const ss2d_scan_fwd_params &p, cudaStream_t stream, CrossInfo xinfo = CrossInfo{0, 0}) {
+static int launch_fwd(const ss2d_scan_fwd_params &p, cudaStream_t stream, CrossInfo xinfo = CrossInfo{0, 0, -1}) {
     using FT = BCTile<in_t, T, SB>;
     constexpr int SLOTS = FT::chunk / SS2D_CKPT_STEPS;
     const int per_g = (int)(p.dim / p.ngroups);
@@ -237,10 +238,10 @@ static int launch_fwd(const ss2d_scan_fwd_params &p, cudaStream_t stream, CrossI
     fl.vec_out = aligned16(p.out) && (!p.out_z || aligned16(p.out_z)) && (p.out_bstride * eo) % 16 == 0 &&
                  (p.out_dstride * eo) % 16 == 0;
     fl.vec_z = p.z && aligned16(p.z) && (p.z_bstride * ei) % 16 == 0 && (p.z_dstride * ei) % 16 == 0;
-    const int64_t grid = p.batch * p.ngroups * tiles;
+    const int64_t grid = p.batch * (xinfo.g_only >= 0 ? 1 : p.ngroups) * tiles;
     auto go = [&](auto kern) -> int {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return (int)e;
+        const int rc = smem_optin(kern, (int)smem);
+        if (rc != 0) return rc;
         kern<<<(unsigned)grid, NW * kWarp, smem, stream>>>(p, tiles, fl, xinfo);
         return (int)cudaGetLastError();
     };
@@ -273,7 +274,7 @@ extern "C" int ss2d_selective_scan_fwd(const ss2d_scan_fwd_params *pp, void *str
     if (p.batch * p.ngroups * (p.dim / p.ngroups) > 0x7fffffffLL) return SS2D_EINVAL;
     if (p.out_dtype != SS2D_F32 && p.out_dtype != p.in_dtype) return SS2D_EDTYPE;
     if (ss2d::sl::supported(p)) return ss2d::sl::launch_fwd(p, reinterpret_cast<cudaStream_t>(stream));
-    return ss2d::dispatch_fwd<false>(p, reinterpret_cast<cudaStream_t>(stream), ss2d::CrossInfo{0, 0});
+    return ss2d::dispatch_fwd<false>(p, reinterpret_cast<cudaStream_t>(stream), ss2d::CrossInfo{0, 0, -1});
 }
 
 // Fused SS2D core forward (seam S3): see ss2d_cross_fwd_params in include/ss2d_b200.h.
@@ -286,7 +287,7 @@ extern "C" int ss2d_cross_scan_fwd(const ss2d_cross_fwd_params *pp, void *stream
     const int64_t L = c.H * c.W;
     ss2d_scan_fwd_params p{};
     p.batch = c.batch; p.dim = 4 * c.D; p.seqlen = L; p.dstate = c.dstate; p.ngroups = 4;
-    p.in_dtype = c.in_dtype; p.out_dtype = SS2D_F32; p.delta_softplus = c.delta_softplus;
+    p.in_dtype = c.in_dtype; p.out_dtype = SS2D_F32; p.delta_softplus = c.delta_softplus; p.family = c.family;
     p.u = c.x; p.delta = c.delta; p.A = c.A; p.B = c.B; p.C = c.C; p.D = c.Dskip; p.delta_bias = c.delta_bias;
     p.u_bstride = c.D * L; p.u_dstride = L;
     p.delta_bstride = 4 * c.D * L; p.delta_dstride = L;
@@ -308,5 +309,14 @@ extern "C" int ss2d_cross_scan_fwd(const ss2d_cross_fwd_params *pp, void *stream
         if (rc != 0) return rc;
         return ss2d::plane_transpose(yT, c.y, c.batch * c.D, (int)c.W, (int)c.H, true, s);
     }
-    return ss2d::dispatch_fwd<true>(p, reinterpret_cast<cudaStream_t>(stream), ss2d::CrossInfo{(int)c.H, (int)c.W});
+    // warp-scan kernels: all four directions accumulate into y.  One launch (sum in arrival order), or — deterministic — one
+    // launch per direction in the order k = 0, 1, 2, 3 (every y element then receives its four terms in that order).
+    // The state-lanes branch above is bit-reproducible as it stands: y and y^T each take exactly two commutative adds onto 0.
+    if (!c.deterministic)
+        return ss2d::dispatch_fwd<true>(p, reinterpret_cast<cudaStream_t>(stream), ss2d::CrossInfo{(int)c.H, (int)c.W, -1});
+    for (int k = 0; k < 4; ++k) {
+        const int rc = ss2d::dispatch_fwd<true>(p, reinterpret_cast<cudaStream_t>(stream), ss2d::CrossInfo{(int)c.H, (int)c.W, k});
+        if (rc != 0) return rc;
+    }
+    return 0;
 }

@@ -319,6 +319,8 @@ static inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t
 
 // does the state-lanes organisation cover this problem?  (everything else runs on the warp-scan kernels)
 bool supported(const ss2d_scan_fwd_params &p);
+// test hook behind ss2d_set_default_family(): what SS2D_FAMILY_AUTO means for this process; returns the old value
+int set_default_family(int family);
 // states per lane for this problem size (the forward and the backward must agree: it fixes nothing in the
 // checkpoint layout, but keeps one place that decides)
 int states_per_lane(const ss2d_scan_fwd_params &p);

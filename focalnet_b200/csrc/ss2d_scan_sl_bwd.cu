@@ -17,7 +17,6 @@
 // issues one scalar atomic per channel per element).  Sums over the 16 states (du, ddelta) are transposed reductions
 // over the channel's lanes.
 #include "ss2d_scan_sl.cuh"
-#include <cstdlib>
 
 namespace ss2d {
 namespace sl {
@@ -497,8 +496,8 @@ static int launch_bwd_t(const ss2d_scan_bwd_params &pb, cudaStream_t stream, Cro
     const int64_t grid = p.batch * p.ngroups * tiles;
     const bool fast = fl.vec_u && fl.vec_delta && fl.vec_bc && fl.vec_dout && fl.vec_dbc && fl.vec_grad && p.seqlen % BK == 0 && !p.z;
     auto go = [&](auto kern) -> int {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM::total);
-        if (e != cudaSuccess) return (int)e;
+        const int rc = smem_optin(kern, (int)SM::total);
+        if (rc != 0) return rc;
         kern<<<(unsigned)grid, NW * kWarp, SM::total, stream>>>(pb, tiles, fl, xi);
         return (int)cudaGetLastError();
     };
@@ -513,12 +512,8 @@ static int launch_bwd_t(const ss2d_scan_bwd_params &pb, cudaStream_t stream, Cro
 template <typename in_t, typename out_t> static int launch_bwd_sn(const ss2d_scan_bwd_params &pb, cudaStream_t s) {
     // 2 states per lane at every size: with 4 the a_t / h_t history of a block needs 128 registers (255 per thread) and
     // the dB/dC staging area 16 KB per warp; measured at B=32, L=16384: 4 warps/CTA 15.7 ms (one CTA per SM), 2 warps/CTA
-    // 9.73 ms, against 9.34 ms for 2 states per lane.  The 4-state build stays reachable through SS2D_SL_SN=4
-    static const bool force4 = [] {
-        const char *e = getenv("SS2D_SL_SN");
-        return e && atoi(e) == 4;
-    }();
-    return force4 ? launch_bwd_t<in_t, out_t, 4, 2>(pb, s) : launch_bwd_t<in_t, out_t, 2>(pb, s);
+    // 9.73 ms, against 9.34 ms for 2 states per lane
+    return launch_bwd_t<in_t, out_t, 2>(pb, s);
 }
 
 int launch_bwd(const ss2d_scan_bwd_params &pb, cudaStream_t s) {

@@ -9,7 +9,7 @@
 // HBM traffic per launch: s_in*(2*B*Dm*L + 2*B*G*N*L) + s_out*B*Dm*L + 4*B*Dm*(ceil(L/16)*N) [block checkpoints]
 //                         + 4*B*Dm*ceil(L/2048)*2N [reference x]
 #include "ss2d_scan_sl.cuh"
-#include <cstdlib>
+#include <atomic>
 
 namespace ss2d {
 namespace sl {
@@ -313,12 +313,16 @@ sl_fwd_cross_kernel(const ss2d_scan_fwd_params p, const int tiles_per_group, con
     sl_fwd_body<float, float, SN, NW, TT, true, true>(p, tiles_per_group, fl, aux);
 }
 
+// process-wide meaning of SS2D_FAMILY_AUTO (test hook ss2d_set_default_family; 0 = by problem size)
+static std::atomic<int> g_default_family{SS2D_FAMILY_AUTO};
+int set_default_family(int f) { return g_default_family.exchange(f >= 0 && f <= 2 ? f : 0); }
+
 bool supported(const ss2d_scan_fwd_params &p) {
     if (p.dstate != kN || p.seqlen > (1LL << 28)) return false;  // step positions and tail byte counts are 32-bit
-    // SS2D_SCAN_IMPL=warpscan / statelanes pins the family (tests, A/B timing); read per call so a test can flip it
-    const char *e = getenv("SS2D_SCAN_IMPL");
-    if (e && e[0] == 'w') return false;
-    if (e && e[0] == 's') return true;
+    int fam = p.family;
+    if (fam != SS2D_FAMILY_STATELANES && fam != SS2D_FAMILY_WARPSCAN) fam = g_default_family.load(std::memory_order_relaxed);
+    if (fam == SS2D_FAMILY_WARPSCAN) return false;
+    if (fam == SS2D_FAMILY_STATELANES) return true;
     // a state-lanes warp walks its whole sequence serially, so the launch takes ~L/4096 * 240 us however few channels
     // there are; the warp-scan kernels scale with the work and win below ~4.6 k channels (measured: B=1 x 768 channels,
     // L=19200: 369 us vs 646 us forward; B=8 x 768, L=4096: 305 us vs 237 us)
@@ -326,11 +330,6 @@ bool supported(const ss2d_scan_fwd_params &p) {
 }
 
 int states_per_lane(const ss2d_scan_fwd_params &p) {
-    static const int force = [] {
-        const char *e = getenv("SS2D_SL_SN");  // development switch
-        return e ? atoi(e) : 0;
-    }();
-    if (force == 2 || force == 4) return force;
     static const int sms = [] {
         int dev = 0, n = 148;
         if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
@@ -364,16 +363,16 @@ static int launch_fwd_t(const ss2d_scan_fwd_params &p, cudaStream_t stream, Cros
     const int64_t grid = p.batch * p.ngroups * tiles;
     const bool fast = fl.vec_u && fl.vec_delta && fl.vec_bc && fl.vec_out && p.seqlen % BK == 0 && !p.z;
     auto go = [&](auto kern) -> int {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM::total);
-        if (e != cudaSuccess) return (int)e;
+        const int rc = smem_optin(kern, (int)SM::total);
+        if (rc != 0) return rc;
         kern<<<(unsigned)grid, NW * kWarp, SM::total, stream>>>(p, tiles, fl);
         return (int)cudaGetLastError();
     };
     if constexpr (CROSS) {
         if (!fast) return SS2D_ESTRIDE;  // covered problem (cross_covered) whose y is not 16-byte aligned
         auto kern = sl_fwd_cross_kernel<SN, NW, TT>;
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM::total);
-        if (e != cudaSuccess) return (int)e;
+        const int rc = smem_optin(kern, (int)SM::total);
+        if (rc != 0) return rc;
         kern<<<(unsigned)grid, NW * kWarp, SM::total, stream>>>(p, tiles, fl, xi);
         return (int)cudaGetLastError();
     } else {
@@ -382,12 +381,9 @@ static int launch_fwd_t(const ss2d_scan_fwd_params &p, cudaStream_t stream, Cros
 }
 
 template <typename in_t, typename out_t> static int launch_fwd_sn(const ss2d_scan_fwd_params &p, cudaStream_t s) {
-    static const int tt = [] {
-        const char *e = getenv("SS2D_SL_TT");  // development switch
-        return e ? atoi(e) : 0;
-    }();
-    if (states_per_lane(p) == 4) return tt == 64 ? launch_fwd_t<in_t, out_t, 4, 4, 64>(p, s) : launch_fwd_t<in_t, out_t, 4, 4, 32>(p, s);
-    return tt == 32 ? launch_fwd_t<in_t, out_t, 2, 4, 32>(p, s) : launch_fwd_t<in_t, out_t, 2, 4, 64>(p, s);
+    // tile of 32 steps with 4 states per lane (3 CTAs/SM by shared memory), 64 steps with 2 (fewer stage barriers)
+    if (states_per_lane(p) == 4) return launch_fwd_t<in_t, out_t, 4, 4, 32>(p, s);
+    return launch_fwd_t<in_t, out_t, 2, 4, 64>(p, s);
 }
 
 int launch_fwd(const ss2d_scan_fwd_params &p, cudaStream_t s) {

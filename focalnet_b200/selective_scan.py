@@ -90,49 +90,64 @@ def _n_ckpt(batch, dim, L, N):
     return int(_lib.lib().ss2d_scan_ckpt_floats(batch, dim, L, N))
 
 
-def _alloc_x_ckpt(u, batch, dim, L, N):
-    """One fp32 buffer = [ x (batch,dim,n_ref,2N) | ckpt workspace | 1 pad word ].
+def _alloc_x_ckpt(u, batch, dim, L, N, family):
+    """One fp32 buffer = [ x (batch,dim,n_ref,2N) | ckpt workspace | `family` pad words ].
 
     ``x`` is the contiguous leading view, so callers that only know the reference contract
     (``last_state = x[:, :, -1, 1::2]``, test_selective_scan.py:79) see exactly the reference tensor, while
     ``scan_bwd`` can find the checkpoints behind it (``_ckpt_of``) even when ``x`` travelled through the
-    reference's own autograd Function (ITS/models/vmamba_layers.py:184,190)."""
+    reference's own autograd Function (ITS/models/vmamba_layers.py:184,190).  The number of pad words (1 or 2) records
+    which kernel family wrote the checkpoints — their layouts differ, and the backward must read them the way the
+    forward wrote them whatever the dispatch rule says at that time."""
     nx, nc = batch * dim * _n_ref(L) * 2 * N, _n_ckpt(batch, dim, L, N)
-    buf = torch.empty(nx + nc + 1, device=u.device, dtype=torch.float32)  # odd size = the signature _ckpt_of checks
+    buf = torch.empty(nx + nc + family, device=u.device, dtype=torch.float32)
     x = buf[:nx].view(batch, dim, _n_ref(L), 2 * N)
     ckpt = buf[nx:nx + nc]
     return x, ckpt
 
 
 def _ckpt_of(x: Optional[torch.Tensor], batch, dim, L, N):
+    """-> (ckpt view, family) behind an ``x`` produced by scan_fwd, or (None, 0) for a foreign tensor."""
     if x is None or x.dtype != torch.float32 or not x.is_cuda:
-        return None
+        return None, 0
     nx, nc = batch * dim * _n_ref(L) * 2 * N, _n_ckpt(batch, dim, L, N)
     if x.storage_offset() != 0 or x.numel() != nx or not x.is_contiguous():
-        return None
-    if x.untyped_storage().nbytes() != (nx + nc + 1) * 4:
-        return None
-    # the odd-sized storage (x | ckpt | 1 tag word) is the signature; no device read, hence no host sync
-    flat = torch.as_strided(x, (nx + nc + 1,), (1,), 0)
-    return flat[nx:nx + nc]
+        return None, 0
+    # the storage size (x | ckpt | 1 or 2 pad words) is the signature; no device read, hence no host sync
+    family = x.untyped_storage().nbytes() // 4 - (nx + nc)
+    if x.untyped_storage().nbytes() % 4 or family not in (_lib.FAMILY_STATELANES, _lib.FAMILY_WARPSCAN):
+        return None, 0
+    flat = torch.as_strided(x, (nx + nc + family,), (1,), 0)
+    return flat[nx:nx + nc], family
 
 
-def scan_fwd(u, delta, A, B, C, D=None, delta_bias=None, delta_softplus=False, nrows=1, out_float=True, z=None):
+class ScanCkpt:
+    """The forward's checkpoint workspace and the kernel family that wrote it (what scan_bwd needs back)."""
+    __slots__ = ("data", "family")
+
+    def __init__(self, data, family):
+        self.data, self.family = data, family
+
+
+def scan_fwd(u, delta, A, B, C, D=None, delta_bias=None, delta_softplus=False, nrows=1, out_float=True, z=None, family=0):
     """-> (out, x, ckpt, out_z).  `fwd` of selective_scan_cuda_oflex (selective_scan_oflex.cpp:157-243) plus the
-    z gate of the API of record.  `nrows` is accepted and ignored like the reference (:236-238)."""
+    z gate of the API of record.  `nrows` is accepted and ignored like the reference (:236-238).  `ckpt` is a ScanCkpt;
+    `family` (tests) pins the kernel family, 0 lets the library choose by problem size."""
     dims = _check_scan_inputs(u, delta, A, B, C, D, delta_bias, z)
     batch, dim, L, N, G = dims
     out_dtype = torch.float32 if out_float else u.dtype
     out = torch.empty((batch, dim, L), device=u.device, dtype=out_dtype)
     out_z = torch.empty_like(out) if z is not None else None
-    x, ckpt = _alloc_x_ckpt(u, batch, dim, L, N)
     P = _lib.ScanFwdParams()
     _fill_fwd(P, u, delta, A, B, C, D, delta_bias, z, delta_softplus, out_dtype, dims)
+    P.family = family
+    P.family = family = int(_lib.lib().ss2d_scan_family(C_byref(P)))  # resolved once; the backward gets the same value
+    x, ckpt = _alloc_x_ckpt(u, batch, dim, L, N, family)
     P.out, P.out_bstride, P.out_dstride = out.data_ptr(), out.stride(0), out.stride(1)
     P.out_z, P.x, P.ckpt = _ptr(out_z), x.data_ptr(), ckpt.data_ptr()
     with torch.cuda.device(u.device):
         _lib.check(_lib.lib().ss2d_selective_scan_fwd(C_byref(P), _stream(u)), "ss2d_selective_scan_fwd")
-    return out, x, ckpt, out_z
+    return out, x, ScanCkpt(ckpt, family), out_z
 
 
 def C_byref(s):
@@ -155,8 +170,10 @@ def scan_bwd(u, delta, A, B, C, D, delta_bias, dout, x=None, delta_softplus=Fals
              "selective_scan: x must be float32 (batch, dim, n_chunks, 2*dstate)")
     if z is not None:
         _chk(out is not None and out.dtype == dout.dtype, "selective_scan: the un-gated out is required with z")
-    if ckpt is None:
-        ckpt = _ckpt_of(x, batch, dim, L, N)
+    if isinstance(ckpt, ScanCkpt):
+        ckpt, family = ckpt.data, ckpt.family
+    else:
+        ckpt, family = _ckpt_of(x, batch, dim, L, N)  # (None, 0) for a foreign x: the library rebuilds the checkpoints
     scratch = None
     if ckpt is None and L > _lib.SL_BLOCK:
         scratch = torch.empty(_n_ckpt(batch, dim, L, N), device=u.device, dtype=torch.float32)
@@ -173,7 +190,7 @@ def scan_bwd(u, delta, A, B, C, D, delta_bias, dout, x=None, delta_softplus=Fals
     _fill_fwd(P.f, u, delta, A, B, C, D, delta_bias, z, delta_softplus, dout.dtype, dims)
     if out is not None:
         P.f.out, P.f.out_bstride, P.f.out_dstride = out.data_ptr(), out.stride(0), out.stride(1)
-    P.f.ckpt = _ptr(ckpt)
+    P.f.ckpt, P.f.family = _ptr(ckpt), family
     P.dout, P.dout_bstride, P.dout_dstride = dout.data_ptr(), dout.stride(0), dout.stride(1)
     P.ckpt_scratch = _ptr(scratch)
     P.du, P.ddelta, P.dz = du.data_ptr(), ddelta.data_ptr(), _ptr(dz)
@@ -192,18 +209,9 @@ def build_selective_scan_fn(mode: str = "ssoflex", out_float: bool = True, tag=N
         @staticmethod
         def forward(ctx, u, delta, A, B, C, D=None, z=None, delta_bias=None, delta_softplus=False,
                     return_last_state=False, nrows=1, backnrows=-1):
-            if u.stride(-1) != 1:
-                u = u.contiguous()
-            if delta.stride(-1) != 1:
-                delta = delta.contiguous()
-            if D is not None:
-                D = D.contiguous()
-            if B.stride(-1) != 1:
-                B = B.contiguous()
-            if C.stride(-1) != 1:
-                C = C.contiguous()
-            if z is not None and z.stride(-1) != 1:
-                z = z.contiguous()
+            # the kernels need unit stride along L only (selective_scan_oflex.cpp:181-182,198-200)
+            u, delta, B, C, z = (t if t is None or t.stride(-1) == 1 else t.contiguous() for t in (u, delta, B, C, z))
+            D = None if D is None else D.contiguous()
             ctx.squeeze_B = B.dim() == 3
             ctx.squeeze_C = C.dim() == 3
             if ctx.squeeze_B:
@@ -224,11 +232,12 @@ def build_selective_scan_fn(mode: str = "ssoflex", out_float: bool = True, tag=N
             ctx.has_z = z is not None
             last_state = x[:, :, -1, 1::2]  # (batch, dim, dstate)
             if ctx.has_z:
-                ctx.save_for_backward(u, delta, A, B, C, D, delta_bias, ckpt, z, out)
+                ctx.save_for_backward(u, delta, A, B, C, D, delta_bias, ckpt.data, z, out)
                 res = out_z
             else:
-                ctx.save_for_backward(u, delta, A, B, C, D, delta_bias, ckpt)
+                ctx.save_for_backward(u, delta, A, B, C, D, delta_bias, ckpt.data)
                 res = out
+            ctx.family = ckpt.family
             if return_last_state:
                 ctx.mark_non_differentiable(last_state)
                 return res, last_state
@@ -243,8 +252,8 @@ def build_selective_scan_fn(mode: str = "ssoflex", out_float: bool = True, tag=N
                 z = out = None
             if dout.stride(-1) != 1:
                 dout = dout.contiguous()
-            du, ddelta, dA, dB, dC, dD, dbias, dz = scan_bwd(u, delta, A, B, C, D, delta_bias, dout, None,
-                                                             ctx.delta_softplus, 1, ckpt=ckpt, z=z, out=out)
+            du, ddelta, dA, dB, dC, dD, dbias, dz = scan_bwd(u, delta, A, B, C, D, delta_bias, dout, None, ctx.delta_softplus, 1,
+                                                             ckpt=ScanCkpt(ckpt, ctx.family), z=z, out=out)
             if ctx.squeeze_B:
                 dB = dB.squeeze(1)
             if ctx.squeeze_C:

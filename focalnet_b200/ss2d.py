@@ -20,7 +20,7 @@ import torch
 import torch.nn.functional as F
 
 from . import _lib
-from .selective_scan import _DT, C_byref, _chk, _n_ckpt, _ptr, _stream, build_selective_scan_fn, scan_bwd, scan_fwd
+from .selective_scan import _DT, C_byref, ScanCkpt, _chk, _n_ckpt, _ptr, _stream, build_selective_scan_fn, scan_bwd, scan_fwd
 
 
 # --------------------------------------------------------------------------------------------- S2
@@ -88,7 +88,8 @@ class _SelectiveScanBase(torch.autograd.Function):
     def _fwd(cls, ctx, u, delta, A, B, Cm, D=None, delta_bias=None, delta_softplus=False, nrows=1, backnrows=1, oflex=True):
         ctx.delta_softplus = delta_softplus
         out, x, ckpt, _ = scan_fwd(u, delta, A, B, Cm, D, delta_bias, delta_softplus, 1, out_float=(oflex and cls.OFLEX))
-        ctx.save_for_backward(u, delta, A, B, Cm, D, delta_bias, ckpt)
+        ctx.save_for_backward(u, delta, A, B, Cm, D, delta_bias, ckpt.data)
+        ctx.family = ckpt.family
         return out
 
     @staticmethod
@@ -97,7 +98,7 @@ class _SelectiveScanBase(torch.autograd.Function):
         if dout.stride(-1) != 1:
             dout = dout.contiguous()
         du, ddelta, dA, dB, dC, dD, dbias, _ = scan_bwd(u, delta, A, B, Cm, D, delta_bias, dout, None, ctx.delta_softplus, 1,
-                                                        ckpt=ckpt)
+                                                        ckpt=ScanCkpt(ckpt, ctx.family))
         return du, ddelta, dA, dB, dC, dD, dbias, None, None, None, None
 
 
@@ -133,7 +134,7 @@ class FusedCrossScanFn(torch.autograd.Function):
     CrossMerge(selective_scan(CrossScan(x), ...)) without the 4x copies (ss2d_cross_scan_fwd/_bwd)."""
 
     @staticmethod
-    def forward(ctx, x, delta, A, Bs, Cs, Ds, delta_bias, delta_softplus=True):
+    def forward(ctx, x, delta, A, Bs, Cs, Ds, delta_bias, delta_softplus=True, deterministic=False):
         B, D, H, W = x.shape
         L, N = H * W, A.shape[1]
         _chk(x.is_cuda and x.dtype in _DT, "fused SS2D core: x must be a CUDA float32/float16/bfloat16 tensor")
@@ -150,20 +151,22 @@ class FusedCrossScanFn(torch.autograd.Function):
         P = _lib.CrossFwdParams()
         FusedCrossScanFn._fill(P, x, delta, A, Bs, Cs, Ds, delta_bias, delta_softplus, (B, D, H, W, N))
         P.y, P.ckpt = y.data_ptr(), ckpt.data_ptr()
-        work = FusedCrossScanFn._work(x, N, L, backward=False)
+        # the family is resolved ONCE here and handed to the backward (the checkpoint layouts of the families differ)
+        P.family = family = int(_lib.lib().ss2d_cross_family(B, D, H, W, N, _DT[x.dtype], 0))
+        P.deterministic = int(bool(deterministic))
+        work = FusedCrossScanFn._work(x, N, L, False, family)
         P.work = _ptr(work)
         with torch.cuda.device(x.device):
             _lib.check(_lib.lib().ss2d_cross_scan_fwd(C_byref(P), _stream(x)), "ss2d_cross_scan_fwd")
         ctx.save_for_backward(x, delta, A, Bs, Cs, Ds, delta_bias, ckpt)
-        ctx.delta_softplus = delta_softplus
+        ctx.delta_softplus, ctx.family, ctx.deterministic = delta_softplus, family, bool(deterministic)
         return y
 
     @staticmethod
-    def _work(x, N, L, backward):
-        """Scratch for the state-lanes kernels (x^T | y^T, resp. x^T | dy^T | dx^T); None selects the warp-scan kernels.
-        The library's rule depends only on dtype / sizes, so the forward and the backward of a problem always agree."""
+    def _work(x, N, L, backward, family):
+        """Scratch for the state-lanes kernels (x^T | y^T, resp. x^T | dy^T | dx^T); None with the warp-scan kernels."""
         B, D, H, W = x.shape
-        n = int(_lib.lib().ss2d_cross_work_floats(B, D, H, W, N, _DT[x.dtype], int(backward)))
+        n = int(_lib.lib().ss2d_cross_work_floats(B, D, H, W, N, _DT[x.dtype], int(backward), family))
         return torch.empty(n, device=x.device, dtype=torch.float32) if n else None
 
     @staticmethod
@@ -190,14 +193,14 @@ class FusedCrossScanFn(torch.autograd.Function):
         dbias = torch.zeros_like(delta_bias) if delta_bias is not None else None
         P = _lib.CrossBwdParams()
         FusedCrossScanFn._fill(P.f, x, delta, A, Bs, Cs, Ds, delta_bias, ctx.delta_softplus, (B, D, H, W, N))
-        P.f.ckpt = ckpt.data_ptr()
-        work = FusedCrossScanFn._work(x, N, L, backward=True)
+        P.f.ckpt, P.f.family, P.f.deterministic = ckpt.data_ptr(), ctx.family, int(ctx.deterministic)
+        work = FusedCrossScanFn._work(x, N, L, True, ctx.family)
         P.f.work = _ptr(work)
         P.dy, P.dx, P.ddelta = dy.data_ptr(), dx.data_ptr(), ddelta.data_ptr()
         P.dA, P.dB, P.dC, P.dDskip, P.ddelta_bias = dA.data_ptr(), dB.data_ptr(), dC.data_ptr(), _ptr(dDs), _ptr(dbias)
         with torch.cuda.device(x.device):
             _lib.check(_lib.lib().ss2d_cross_scan_bwd(C_byref(P), _stream(x)), "ss2d_cross_scan_bwd")
-        return dx.view(B, D, H, W).to(x.dtype), ddelta, dA, dB.to(Bs.dtype), dC.to(Cs.dtype), dDs, dbias, None
+        return dx.view(B, D, H, W).to(x.dtype), ddelta, dA, dB.to(Bs.dtype), dC.to(Cs.dtype), dDs, dbias, None, None
 
 
 class MergeNormGateFn(torch.autograd.Function):
@@ -304,8 +307,11 @@ def cross_selective_scan(
     dt_low_rank=True,
 ):
     """Drop-in for the reference ``cross_selective_scan`` (vmamba_layers.py:200-299): same arguments, same
-    (B,H,W,D) result.  ``SelectiveScan`` / ``CrossScan`` / ``CrossMerge`` / ``nrows`` / ``no_einsum`` select
-    implementations in the reference; here they are accepted and ignored — there is one implementation.
+    (B,H,W,D) result.  ``SelectiveScan`` / ``CrossScan`` / ``CrossMerge`` / ``nrows`` / ``backnrows`` select
+    implementations in the reference; here they are accepted and ignored — there is one implementation.  The flags
+    that change NUMERICS are honoured like the reference: ``force_fp32`` (cast x / dts / Bs / Cs to float after the
+    projections, :281-285), ``no_einsum`` (projections through 1x1 conv1d = cuDNN and its TF32 policy, else through
+    einsum = cuBLAS and its policy, :260-270), ``ssoflex`` (fp32 scan output, else the input dtype), ``to_dtype``.
 
     x_proj is pointwise over pixels, so x_dbl_k = W_k x is computed ONCE from x in spatial order and only that
     38-row tensor is permuted into each direction's scan order; x itself (192 rows) is read by the scan kernel
@@ -315,23 +321,35 @@ def cross_selective_scan(
     K, _, R = dt_projs_weight.shape
     L = H * W
     _chk(K == 4 and dt_low_rank, "fused SS2D core supports the 4-direction low-rank-dt configuration of the model")
-    xin = x.float() if force_fp32 else x
-    xf = xin.reshape(B, D, L)
-    # the two projections stay on the reference's own library call, 1x1 conv1d (vmamba_layers.py:262-264): same cuDNN
-    # kernels and the same TF32 policy (torch.backends.cudnn.allow_tf32) as the code this replaces — x_proj un-grouped,
-    # because all four directions read the same spatial-order x
-    x_dbl = F.conv1d(xf, x_proj_weight.reshape(K * (R + 2 * N), D, 1).to(xf.dtype),
-                     None if x_proj_bias is None else x_proj_bias.reshape(-1).to(xf.dtype))  # (B, K*(R+2N), L) spatial
-    x_dbl = _to_scan_order(x_dbl.view(B, K, R + 2 * N, L), H, W)
+    xf = x.reshape(B, D, L)
+    C_all = K * (R + 2 * N)
+    # the two projections stay on the reference's own library calls (vmamba_layers.py:262-270), run in x's dtype like
+    # there — x_proj un-grouped, because all four directions read the same spatial-order x
+    if no_einsum:
+        x_dbl = F.conv1d(xf, x_proj_weight.reshape(C_all, D, 1), None if x_proj_bias is None else x_proj_bias.reshape(-1))
+    else:
+        x_dbl = torch.einsum("b d l, c d -> b c l", xf, x_proj_weight.reshape(C_all, D))
+        if x_proj_bias is not None:
+            x_dbl = x_dbl + x_proj_bias.reshape(1, -1, 1)
+    x_dbl = _to_scan_order(x_dbl.view(B, K, R + 2 * N, L), H, W)        # (B, K, R+2N, L), each direction's scan order
     dts_lr, Bs, Cs = torch.split(x_dbl, [R, N, N], dim=2)
-    dts = F.conv1d(dts_lr.reshape(B, K * R, L), dt_projs_weight.reshape(K * D, R, 1).to(x_dbl.dtype), groups=K)  # scan order
+    if no_einsum:
+        dts = F.conv1d(dts_lr.reshape(B, K * R, L), dt_projs_weight.reshape(K * D, R, 1), groups=K)
+    else:
+        dts = torch.einsum("b k r l, k d r -> b k d l", dts_lr, dt_projs_weight).reshape(B, K * D, L)
     As = -torch.exp(A_logs.to(torch.float))
+    xin = x
+    if force_fp32:  # vmamba_layers.py:281-285
+        xin, dts, Bs, Cs = xin.to(torch.float), dts.to(torch.float), Bs.to(torch.float), Cs.to(torch.float)
     y = FusedCrossScanFn.apply(xin, dts, As, Bs, Cs, Ds.to(torch.float), dt_projs_bias.reshape(-1).to(torch.float),
                                delta_softplus)
+    if not ssoflex:
+        y = y.to(xin.dtype)  # SSOflex with oflex=False / SSCore return the scan output in the input dtype
     if out_norm_shape in ["v1"]:
         y = out_norm(y.view(B, -1, H, W)).permute(0, 2, 3, 1)
-    elif isinstance(out_norm, torch.nn.LayerNorm) and out_norm.elementwise_affine and out_norm.bias is not None and \
-            tuple(out_norm.normalized_shape) == (D,) and D <= 512:
+    elif y.dtype == torch.float32 and isinstance(out_norm, torch.nn.LayerNorm) and out_norm.elementwise_affine and \
+            out_norm.bias is not None and out_norm.weight.dtype == torch.float32 and tuple(out_norm.normalized_shape) == (D,) \
+            and D <= 512 and not torch.is_autocast_enabled():
         # transpose + LayerNorm in one kernel (row N1 of SURVEY §8f) instead of a transpose copy + ATen LayerNorm
         y = merge_norm_gate(y, out_norm.weight, out_norm.bias, out_norm.eps).view(B, H, W, -1)
     else:
@@ -339,10 +357,36 @@ def cross_selective_scan(
     return y.to(x.dtype) if to_dtype else y
 
 
+def block_supported(m: torch.nn.Module) -> bool:
+    """True when ``ss2d_forward`` computes exactly what this (unchanged reference) SS2D module's forwardv2 does: the
+    shipped ITS configuration — forward type v4 (force_fp32=False, no_einsum, ssoflex), 3x3 depthwise conv with bias,
+    SiLU on x and z, z gate, LayerNorm(d_inner) in channels-last ("v0"), fp32 parameters, no dropout."""
+    try:
+        fc = m.forward_core
+        kw = getattr(fc, "keywords", {}) or {}
+        conv = m.conv2d
+        return (
+            m.d_conv == 3 and not m.disable_z and not m.disable_z_act and isinstance(m.act, torch.nn.SiLU)
+            and m.out_norm_shape == "v0" and isinstance(m.out_norm, torch.nn.LayerNorm) and m.out_norm.elementwise_affine
+            and m.out_norm.bias is not None and tuple(m.out_norm.normalized_shape) == (conv.out_channels,)
+            and conv.out_channels <= 512 and conv.kernel_size == (3, 3) and conv.padding == (1, 1)
+            and conv.groups == conv.in_channels == conv.out_channels and conv.bias is not None
+            and isinstance(m.dropout, torch.nn.Identity) and m.in_proj.weight.dtype == torch.float32
+            and m.dt_projs_weight.shape[0] == 4 and m.A_logs.shape[1] == 16
+            and not kw.get("force_fp32", False) and kw.get("no_einsum", False)
+        )
+    except AttributeError:
+        return False
+
+
 def ss2d_forward(m: torch.nn.Module, x: torch.Tensor) -> torch.Tensor:
     """SS2D.forwardv2 (vmamba_layers.py:583-601) on this library's kernels, for an *unchanged* reference SS2D module `m`
-    (fp32, d_conv == 3, LayerNorm out_norm, z gate with SiLU): in_proj -> dwconv3x3+SiLU pre-mix (no permute copy) ->
-    fused 4-direction scan -> transpose+LayerNorm+z-gate epilogue (one kernel) -> out_proj."""
+    in the configuration ``block_supported`` describes: in_proj -> dwconv3x3+SiLU pre-mix (no permute copy) -> fused
+    4-direction scan -> transpose+LayerNorm+z-gate epilogue (one kernel) -> out_proj.  Any other configuration (or an
+    autocast region, where the reference would run the conv / LayerNorm in 16 bits) takes the module's own forwardv2
+    with the fused core."""
+    if not block_supported(m) or torch.is_autocast_enabled() or x.dtype != torch.float32:
+        return m.forwardv2(x)
     xz = m.in_proj(x)                                        # (B, H, W, 2*d_inner)
     B, H, W, _ = xz.shape
     D = m.conv2d.out_channels
@@ -359,14 +403,35 @@ def ss2d_forward(m: torch.nn.Module, x: torch.Tensor) -> torch.Tensor:
     return m.dropout(m.out_proj(y))
 
 
-def patch_ss2d(model: torch.nn.Module) -> int:
-    """Re-bind ``forward_core`` (an instance attribute, vmamba_layers.py:451) of every SS2D module of an unchanged
-    reference model to the fused path via the ``cross_selective_scan=`` hook of forward_corev2 (:566).  Returns the
-    number of modules patched."""
+def patch_ss2d(model: torch.nn.Module, fuse_block: bool = True) -> int:
+    """Put every SS2D module of an *unchanged* reference model on this library, without editing ITS/models:
+
+    * ``forward_core`` (an instance attribute, vmamba_layers.py:451) is re-bound to the module's OWN partial with the
+      ``cross_selective_scan=`` hook of forward_corev2 (:566) pointing at the fused core — the module's force_fp32 /
+      no_einsum / ssoflex choices (:444-449) are kept;
+    * with ``fuse_block`` and a module in the shipped configuration (``block_supported``), ``forward`` (also an instance
+      attribute, :403) is re-bound to ``ss2d_forward``: the dwconv+SiLU pre-mix and the LayerNorm+gate epilogue run on
+      this library's kernels too.
+
+    Returns the number of modules patched; ``unpatch_ss2d`` restores them."""
     n = 0
     for m in model.modules():
-        if hasattr(m, "forward_corev2") and hasattr(m, "forward_core"):
-            m.forward_core = partial(m.forward_corev2, cross_selective_scan=cross_selective_scan)
+        if hasattr(m, "forward_corev2") and callable(getattr(m, "forward_core", None)):
+            if not hasattr(m, "_ss2d_b200_orig"):
+                m._ss2d_b200_orig = (m.forward_core, m.forward)
+            core, fwd = m._ss2d_b200_orig
+            m.forward_core = partial(core, cross_selective_scan=cross_selective_scan)
+            m.forward = partial(ss2d_forward, m) if (fuse_block and block_supported(m)) else fwd
+            n += 1
+    return n
+
+
+def unpatch_ss2d(model: torch.nn.Module) -> int:
+    n = 0
+    for m in model.modules():
+        if hasattr(m, "_ss2d_b200_orig"):
+            m.forward_core, m.forward = m._ss2d_b200_orig
+            del m._ss2d_b200_orig
             n += 1
     return n
 
@@ -410,28 +475,3 @@ class DwConvSiLUFn(torch.autograd.Function):
 
 def dwconv_silu(xz, weight, bias=None, channels=None):
     return DwConvSiLUFn.apply(xz, weight, bias, channels or weight.shape[0])
-
-
-def smoke_fused():
-    """One tiny fused forward+backward on cuda:0 checked against the CPU oracle (called by __graft_entry__.smoke)."""
-    import numpy as np
-    from oracle import ss2d_oracle as orc
-    g = torch.Generator().manual_seed(3)
-    import os
-    B, D, H, W, N = 1, 8, 8, 10, 16
-    L = H * W
-    x = torch.randn(B, D, H, W, generator=g).cuda()
-    delta = (0.5 * torch.rand(B, 4 * D, L, generator=g)).cuda()
-    A = (-0.5 * torch.rand(4 * D, N, generator=g)).cuda()
-    Bs, Cs = torch.randn(B, 4, N, L, generator=g).cuda(), torch.randn(B, 4, N, L, generator=g).cuda()
-    Ds, bias = torch.randn(4 * D, generator=g).cuda(), (0.5 * torch.rand(4 * D, generator=g)).cuda()
-    xs = orc.cross_scan(x).reshape(B, 4 * D, L)
-    f = orc.scan_fwd(xs, delta, A, Bs, Cs, Ds, None, bias, True)
-    ref = orc.cross_merge(f["out"].reshape(B, 4, D, H, W))
-    for family in ("statelanes", "warpscan"):  # pin each kernel family in turn (the default rule goes by problem size)
-        os.environ["SS2D_SCAN_IMPL"] = family
-        y = FusedCrossScanFn.apply(x, delta, A, Bs, Cs, Ds, bias, True)
-        err = float(np.abs(y.cpu().numpy() - ref).max() / np.abs(ref).max())
-        print(f"[smoke] fused SS2D core ({family}) vs CPU oracle: max rel err {err:.2e}")
-        assert err < 1e-3, err
-    os.environ.pop("SS2D_SCAN_IMPL", None)

@@ -31,10 +31,16 @@
 extern "C" {
 #endif
 
-#define SS2D_ABI_VERSION 2
+#define SS2D_ABI_VERSION 3
 
 /* element types of u / delta / B / C / z (in_dtype) and of out / dout (out_dtype) */
 enum { SS2D_F32 = 0, SS2D_F16 = 1, SS2D_BF16 = 2 };
+
+/* Kernel family that serves a scan (field `family` of the parameter structs).  The two families keep their checkpoints
+ * in different layouts, so the forward and the backward of one problem MUST run on the same family: callers pass
+ * SS2D_FAMILY_AUTO to the forward, read the choice back with ss2d_scan_family() and hand that value to the backward.
+ * A pinned family that does not cover the shape (state-lanes needs dstate == 16) falls through to the other one. */
+enum { SS2D_FAMILY_AUTO = 0, SS2D_FAMILY_STATELANES = 1, SS2D_FAMILY_WARPSCAN = 2 };
 
 /* negative return codes (argument validation, nothing was launched) */
 enum {
@@ -69,7 +75,7 @@ enum {
  * ------------------------------------------------------------------------------------------- */
 typedef struct ss2d_scan_fwd_params {
     int64_t batch, dim, seqlen, dstate, ngroups;
-    int32_t in_dtype, out_dtype, delta_softplus, reserved0;
+    int32_t in_dtype, out_dtype, delta_softplus, family;
     const void *u, *delta;
     const float *A;
     const void *B, *C;
@@ -107,8 +113,15 @@ const char *ss2d_build_info(void);
 /* human-readable text for a return code of this library (negative) or of CUDA (positive) */
 const char *ss2d_error_string(int code);
 
-/* number of f32 elements of the `ckpt` workspace for a scan of this shape (0 on invalid sizes) */
+/* number of f32 elements of the `ckpt` workspace for a scan of this shape (0 on invalid sizes); one size serves
+ * whichever family takes the shape */
 int64_t ss2d_scan_ckpt_floats(int64_t batch, int64_t dim, int64_t seqlen, int64_t dstate);
+/* the family (SS2D_FAMILY_STATELANES / _WARPSCAN) that serves a scan with these sizes / dtypes and this `family` request;
+ * only batch, dim, seqlen, dstate, ngroups and family are read */
+int ss2d_scan_family(const ss2d_scan_fwd_params *p);
+/* TEST HOOK: what SS2D_FAMILY_AUTO resolves to for the whole process — 0 (default): by problem size; 1 / 2: that family.
+ * Returns the previous value.  The product path never calls it (there is no environment switch). */
+int ss2d_set_default_family(int family);
 
 int ss2d_selective_scan_fwd(const ss2d_scan_fwd_params *p, void *stream);
 int ss2d_selective_scan_bwd(const ss2d_scan_bwd_params *p, void *stream);
@@ -140,6 +153,11 @@ int ss2d_cross_permute(const void *src, void *dst, int64_t B, int64_t C, int64_t
 typedef struct ss2d_cross_fwd_params {
     int64_t batch, D, H, W, dstate;
     int32_t in_dtype, delta_softplus;
+    int32_t family;        /* SS2D_FAMILY_*: as in ss2d_scan_fwd_params (ss2d_cross_family() reports the choice)          */
+    int32_t deterministic; /* != 0: y / dx are bit-reproducible run to run, like triton_cross_merge (csm_triton.py:45-80).
+                              State-lanes kernels: always (y and y^T each take two commutative adds onto zero, then one
+                              transposing add: y = (y0 + y2) + (y1 + y3)).  Warp-scan kernels: one launch per direction in
+                              the order k = 0, 1, 2, 3 instead of one launch whose red.global.add arrive in any order.   */
     const void *x, *delta, *B, *C;
     const float *A, *Dskip, *delta_bias;
     float *y;
@@ -170,7 +188,10 @@ typedef struct ss2d_cross_bwd_params {
 
 /* f32 elements of `work`: 2*batch*D*H*W for the forward, 3*batch*D*H*W for the backward; 0 when the state-lanes
  * kernels do not take the problem (not fp32, dstate != 16, H*W % 16 != 0, fewer than ~4.6 k channel sequences) */
-int64_t ss2d_cross_work_floats(int64_t batch, int64_t D, int64_t H, int64_t W, int64_t dstate, int32_t in_dtype, int32_t backward);
+int64_t ss2d_cross_work_floats(int64_t batch, int64_t D, int64_t H, int64_t W, int64_t dstate, int32_t in_dtype, int32_t backward,
+                               int32_t family);
+/* family serving the fused problem (given `work` is supplied as ss2d_cross_work_floats asks) */
+int ss2d_cross_family(int64_t batch, int64_t D, int64_t H, int64_t W, int64_t dstate, int32_t in_dtype, int32_t family);
 /* src: `planes` images of (H, W) -> dst: images of (W, H); dst = src^T, or dst += src^T when accumulate != 0 */
 int ss2d_plane_transpose(const float *src, float *dst, int64_t planes, int64_t H, int64_t W, int32_t accumulate, void *stream);
 

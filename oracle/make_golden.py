@@ -67,6 +67,8 @@ def load_reference():
 
 
 def scan_case(tss, name, Bn, Dm, N, L, G, has_D, has_z, has_bias, softplus, seed, squeeze_bc=False):
+    if os.environ.get("ONLY") and os.environ["ONLY"] not in f"scan_{name}":
+        return
     # input distributions of test_selective_scan.py:406-441
     g = torch.Generator().manual_seed(seed)
     A = (-0.5 * torch.rand(Dm, N, generator=g)).requires_grad_()
@@ -97,6 +99,8 @@ def scan_case(tss, name, Bn, Dm, N, L, G, has_D, has_z, has_bias, softplus, seed
 
 
 def cross_cases(vml):
+    if os.environ.get("ONLY") and os.environ["ONLY"] not in "cross":
+        return
     g = torch.Generator().manual_seed(7)
     rec = {}
     for tag, (B, C, H, W) in dict(a=(2, 3, 5, 7), b=(1, 2, 8, 8), c=(1, 1, 1, 6)).items():
@@ -110,6 +114,12 @@ def cross_cases(vml):
 
 
 def fused_case(tss, vml, name, B, D, H, W, N, R, seed):
+    if os.environ.get("ONLY") and os.environ["ONLY"] not in f"fused_{name}":
+        return
+    _fused_case(tss, vml, name, B, D, H, W, N, R, seed)
+
+
+def _fused_case(tss, vml, name, B, D, H, W, N, R, seed):
     """cross_selective_scan (vmamba_layers.py:200-299) with the CPU pieces the reference itself ships:
     torch CrossScan/CrossMerge + a Function wrapping selective_scan_ref."""
     K = 4
@@ -150,6 +160,8 @@ def fused_case(tss, vml, name, B, D, H, W, N, R, seed):
 
 def dwconv_case():
     """SS2D.forwardv2 pre-mix (vmamba_layers.py:585-594): chunk -> permute -> depthwise conv3x3+bias -> SiLU."""
+    if os.environ.get("ONLY") and os.environ["ONLY"] not in "dwconv":
+        return
     g = torch.Generator().manual_seed(11)
     B, H, W, C = 2, 6, 5, 8
     xz = torch.randn(B, H, W, 2 * C, generator=g).requires_grad_()
@@ -178,4 +190,7 @@ if __name__ == "__main__":
     cross_cases(vml)
     fused_case(tss, vml, "small", 2, 8, 5, 7, 4, 2, 21)
     fused_case(tss, vml, "n16", 1, 12, 6, 6, 16, 3, 22)
+    # L % 16 == 0 (round 2): shapes the state-lanes fused kernels (fp32, dstate 16, whole 16-step blocks) take when pinned
+    fused_case(tss, vml, "n16_8x8", 1, 8, 8, 8, 16, 3, 23)
+    fused_case(tss, vml, "n16_4x12", 2, 20, 4, 12, 16, 6, 24)
     dwconv_case()

@@ -20,12 +20,16 @@ def golden_dir():
 
 
 @pytest.fixture(params=["statelanes", "warpscan"])
-def scan_family(request, monkeypatch):
+def scan_family(request):
     """Runs a GPU test once per scan-kernel family.  The library picks the family by problem size (state-lanes from
-    ~4.6 k channel sequences of dstate 16, warp-scan otherwise); SS2D_SCAN_IMPL pins it so that the small parity shapes
-    exercise both (shapes a family does not cover, e.g. dstate != 16, fall through to the other one)."""
-    monkeypatch.setenv("SS2D_SCAN_IMPL", request.param)
-    return request.param
+    ~4.6 k channel sequences of dstate 16, warp-scan otherwise); the test hook ss2d_set_default_family pins what "auto"
+    means so that the small parity shapes exercise both (shapes a family does not cover, e.g. dstate != 16, fall through
+    to the other one)."""
+    from focalnet_b200 import _lib
+    fam = {"statelanes": _lib.FAMILY_STATELANES, "warpscan": _lib.FAMILY_WARPSCAN}[request.param]
+    old = _lib.lib().ss2d_set_default_family(fam)
+    yield request.param
+    _lib.lib().ss2d_set_default_family(old)
 
 
 @pytest.fixture(autouse=True)

@@ -26,7 +26,7 @@ def test_every_declared_symbol_is_exported(lib):
     assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.ss2d_abi_version() == 2
+    assert lib.ss2d_abi_version() == 3
     assert b"sm_100a" in lib.ss2d_build_info()
     assert b"invalid" in lib.ss2d_error_string(-22)
     # checkpoint workspace: state-lanes layout (h every 16 steps) for dstate 16, coarse layout otherwise
@@ -34,10 +34,27 @@ def test_every_declared_symbol_is_exported(lib):
     assert lib.ss2d_scan_ckpt_floats(2, 8, 1000, 4) == 2 * 8 * 4 * 4
     assert lib.ss2d_scan_ckpt_floats(0, 8, 1000, 4) == 0
     # fused-seam scratch: only fp32 / dstate 16 / L % 16 == 0 / enough channel sequences run on the state-lanes kernels
-    assert lib.ss2d_cross_work_floats(8, 192, 64, 64, 16, 0, 0) == 2 * 8 * 192 * 4096
-    assert lib.ss2d_cross_work_floats(8, 192, 64, 64, 16, 0, 1) == 3 * 8 * 192 * 4096
-    assert lib.ss2d_cross_work_floats(8, 192, 64, 64, 8, 0, 0) == 0 and lib.ss2d_cross_work_floats(8, 192, 64, 64, 16, 2, 0) == 0
-    assert lib.ss2d_cross_work_floats(8, 192, 17, 23, 16, 0, 0) == 0 and lib.ss2d_cross_work_floats(1, 192, 64, 64, 16, 0, 0) == 0
+    assert lib.ss2d_cross_work_floats(8, 192, 64, 64, 16, 0, 0, 0) == 2 * 8 * 192 * 4096
+    assert lib.ss2d_cross_work_floats(8, 192, 64, 64, 16, 0, 1, 0) == 3 * 8 * 192 * 4096
+    assert lib.ss2d_cross_work_floats(8, 192, 64, 64, 8, 0, 0, 0) == 0 and lib.ss2d_cross_work_floats(8, 192, 64, 64, 16, 2, 0, 0) == 0
+    assert lib.ss2d_cross_work_floats(8, 192, 17, 23, 16, 0, 0, 0) == 0 and lib.ss2d_cross_work_floats(1, 192, 64, 64, 16, 0, 0, 0) == 0
+    # kernel family: by problem size unless pinned (in the params, or process-wide through the test hook); a pinned
+    # family that does not cover the shape falls through
+    p = _lib.ScanFwdParams()
+    p.batch, p.dim, p.seqlen, p.dstate, p.ngroups = 8, 768, 4096, 16, 4
+    fam = lambda: lib.ss2d_scan_family(ctypes.cast(ctypes.pointer(p), ctypes.c_void_p))
+    assert fam() == _lib.FAMILY_STATELANES
+    p.batch = 1
+    assert fam() == _lib.FAMILY_WARPSCAN
+    p.family = _lib.FAMILY_STATELANES
+    assert fam() == _lib.FAMILY_STATELANES
+    p.dstate = 8
+    assert fam() == _lib.FAMILY_WARPSCAN
+    p.dstate, p.family = 16, 0
+    assert lib.ss2d_set_default_family(_lib.FAMILY_STATELANES) == 0 and fam() == _lib.FAMILY_STATELANES
+    assert lib.ss2d_set_default_family(0) == _lib.FAMILY_STATELANES and fam() == _lib.FAMILY_WARPSCAN
+    assert lib.ss2d_cross_family(1, 192, 64, 64, 16, 0, _lib.FAMILY_STATELANES) == _lib.FAMILY_STATELANES
+    assert lib.ss2d_cross_family(8, 192, 64, 60, 16, 2, 0) == _lib.FAMILY_WARPSCAN
 
 
 def test_struct_layout_matches_header(lib):
@@ -45,7 +62,7 @@ def test_struct_layout_matches_header(lib):
     from focalnet_b200 import _lib
     assert ctypes.sizeof(_lib.ScanFwdParams) == 5 * 8 + 4 * 4 + 8 * 8 + 12 * 8 + 8 + 16 + 8 * 3
     assert ctypes.sizeof(_lib.ScanBwdParams) == ctypes.sizeof(_lib.ScanFwdParams) + 8 + 16 + 8 + 8 * 8
-    assert ctypes.sizeof(_lib.CrossFwdParams) == 5 * 8 + 2 * 4 + 9 * 8 + 2 * 8 + 8
+    assert ctypes.sizeof(_lib.CrossFwdParams) == 5 * 8 + 4 * 4 + 9 * 8 + 2 * 8 + 8
     assert ctypes.sizeof(_lib.CrossBwdParams) == ctypes.sizeof(_lib.CrossFwdParams) + 9 * 8
 
 

@@ -51,7 +51,7 @@ def test_cross_scan_merge_vs_oracle_and_autograd(shape, dt):
     assert torch.equal(ys.grad.float().cpu().reshape(B, 4, C, H * W), torch.from_numpy(orc.cross_scan(gm.float().view(B, C, H, W))))
 
 
-@pytest.mark.parametrize("name", ["small", "n16"])
+@pytest.mark.parametrize("name", ["small", "n16", "n16_8x8", "n16_4x12"])  # the last two: L % 16 == 0 (state-lanes fused kernels)
 def test_fused_core_matches_reference_golden(name):
     """cross_selective_scan (vmamba_layers.py:200-299) executed by the Python reference on CPU vs our fused path."""
     from focalnet_b200 import cross_selective_scan

@@ -159,6 +159,81 @@ __global__ void k_lds_shfl(float *out, float seed) {
     float s = acc.x + acc.y + acc.z + acc.w; for (int i = 0; i < 4 * ILP; ++i) s += v[i];
     if (s == 123.456f) out[0] = s;
 }
+
+// LDS address-pattern study (round 2): does a broadcast (few distinct addresses per warp) cost fewer data-pipe cycles?
+//   MODE 0: every lane its own 16 bytes (512 B per instruction)        MODE 1: all lanes the same 16 bytes
+//   MODE 2: lane/8 -> 4 distinct addresses (xch pattern)                MODE 3: lane%8 -> 8 distinct addresses (B/C pattern)
+//   MODE 4: lane%2 -> 2 distinct addresses                              MODE 5: lane/16 -> 2 distinct addresses
+template <int MODE, typename V> __global__ void k_lds_pat(float *out, float seed) {
+    __shared__ float4 sm[1024];
+    for (int i = threadIdx.x; i < 1024; i += blockDim.x) sm[i] = make_float4(seed, seed, seed, seed);
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    int idx = MODE == 0 ? lane : MODE == 1 ? 0 : MODE == 2 ? lane / 8 : MODE == 3 ? lane % 8 : MODE == 4 ? lane % 2 : lane / 16;
+    idx += (threadIdx.x >> 5) * 37;
+    float acc = 0.f;
+    const V *base = reinterpret_cast<const V *>(sm);
+    constexpr int PER = sizeof(float4) / sizeof(V);
+    for (int it = 0; it < ITERS; ++it) {
+#pragma unroll
+        for (int i = 0; i < ILP; ++i) {
+            V t = base[((idx + i * 32) & 1023) * PER];
+            if constexpr (sizeof(V) == 16) acc += (t.x + t.y) + (t.z + t.w);
+            else if constexpr (sizeof(V) == 8) acc += t.x + t.y;
+            else acc += t;
+        }
+        idx += 1;
+    }
+    if (acc == 123.456f) out[0] = acc;
+}
+// STS.128, every lane its own 16 bytes
+__global__ void k_sts128(float *out, float seed) {
+    __shared__ float4 sm[2048];
+    float4 v = make_float4(seed, seed + threadIdx.x, seed, seed);
+    int idx = threadIdx.x;
+    for (int it = 0; it < ITERS; ++it) {
+#pragma unroll
+        for (int i = 0; i < ILP; ++i) sm[(idx + i * 256) & 2047] = v;
+        v.x += 1.f;
+    }
+    __syncthreads();
+    if (sm[threadIdx.x].x == 123.456f) out[0] = 1.f;
+}
+// packed half-precision exponentials: one MUFU instruction, two results
+__global__ void k_mufu_h2(float *out, float seed) {
+    unsigned v[ILP];
+#pragma unroll
+    for (int i = 0; i < ILP; ++i) v[i] = 0x38003800u + i + threadIdx.x;
+    for (int it = 0; it < ITERS; ++it) {
+#pragma unroll
+        for (int i = 0; i < ILP; ++i) asm volatile("ex2.approx.f16x2 %0, %0;" : "+r"(v[i]));
+    }
+    unsigned s = 0; for (int i = 0; i < ILP; ++i) s += v[i];
+    if (s == 123456u) out[0] = 1.f;
+}
+__global__ void k_mufu_bf2(float *out, float seed) {
+    unsigned v[ILP];
+#pragma unroll
+    for (int i = 0; i < ILP; ++i) v[i] = 0x3f003f00u + i + threadIdx.x;
+    for (int it = 0; it < ITERS; ++it) {
+#pragma unroll
+        for (int i = 0; i < ILP; ++i) asm volatile("ex2.approx.ftz.bf16x2 %0, %0;" : "+r"(v[i]));
+    }
+    unsigned s = 0; for (int i = 0; i < ILP; ++i) s += v[i];
+    if (s == 123456u) out[0] = 1.f;
+}
+// FSEL (ALU pipe) rate, and FSEL interleaved with FFMA (do they dual-issue on separate pipes?)
+__global__ void k_fsel(float *out, float seed) {
+    float v[ILP]; const bool up = (threadIdx.x & 4) != 0;
+#pragma unroll
+    for (int i = 0; i < ILP; ++i) v[i] = seed + i + threadIdx.x;
+    for (int it = 0; it < ITERS; ++it) {
+#pragma unroll
+        for (int i = 0; i < ILP; ++i) { const float a = v[i], b = v[(i + 3) % ILP]; v[i] = up ? a : b; }
+    }
+    float s = 0; for (int i = 0; i < ILP; ++i) s += v[i];
+    if (s == 123.456f) out[0] = s;
+}
 template <typename F> float time_ms(F f, int n = 5) {
     cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
     f(); cudaDeviceSynchronize();
@@ -192,6 +267,22 @@ int main() {
     rep("SHFL.UP", time_ms([&] { k_shfl<<<blocks, threads>>>(out, 0.5f); }), 1);
     rep("LDS.128 (conflict-free)", time_ms([&] { k_lds128<<<blocks, threads>>>(out, 0.5f); }), 1);
     rep("1 LDS.128 + 4 SHFL (total)", time_ms([&] { k_lds_shfl<<<blocks, threads>>>(out, 0.5f); }), 5);
+
+    rep("LDS.128 lane-distinct", time_ms([&] { k_lds_pat<0, float4><<<blocks, threads>>>(out, 0.5f); }), 1);
+    rep("LDS.128 uniform address", time_ms([&] { k_lds_pat<1, float4><<<blocks, threads>>>(out, 0.5f); }), 1);
+    rep("LDS.128 4 addr (lane/8)", time_ms([&] { k_lds_pat<2, float4><<<blocks, threads>>>(out, 0.5f); }), 1);
+    rep("LDS.128 8 addr (lane%8)", time_ms([&] { k_lds_pat<3, float4><<<blocks, threads>>>(out, 0.5f); }), 1);
+    rep("LDS.128 2 addr (lane%2)", time_ms([&] { k_lds_pat<4, float4><<<blocks, threads>>>(out, 0.5f); }), 1);
+    rep("LDS.128 2 addr (lane/16)", time_ms([&] { k_lds_pat<5, float4><<<blocks, threads>>>(out, 0.5f); }), 1);
+    rep("LDS.64 lane-distinct", time_ms([&] { k_lds_pat<0, float2><<<blocks, threads>>>(out, 0.5f); }), 1);
+    rep("LDS.64 uniform address", time_ms([&] { k_lds_pat<1, float2><<<blocks, threads>>>(out, 0.5f); }), 1);
+    rep("LDS.64 8 addr (lane%8)", time_ms([&] { k_lds_pat<3, float2><<<blocks, threads>>>(out, 0.5f); }), 1);
+    rep("LDS.32 lane-distinct", time_ms([&] { k_lds_pat<0, float><<<blocks, threads>>>(out, 0.5f); }), 1);
+    rep("LDS.32 uniform address", time_ms([&] { k_lds_pat<1, float><<<blocks, threads>>>(out, 0.5f); }), 1);
+    rep("STS.128 lane-distinct", time_ms([&] { k_sts128<<<blocks, threads>>>(out, 0.5f); }), 1);
+    rep("MUFU.EX2 f16x2 (per instr)", time_ms([&] { k_mufu_h2<<<blocks, threads>>>(out, 0.5f); }), 1);
+    rep("MUFU.EX2 bf16x2 (per instr)", time_ms([&] { k_mufu_bf2<<<blocks, threads>>>(out, 0.5f); }), 1);
+    rep("FSEL", time_ms([&] { k_fsel<<<blocks, threads>>>(out, 0.5f); }), 1);
     // reductions: 64 MB window (fits L2), 16 M threads x reps
     size_t n = 16u << 20; float *buf; CK(cudaMalloc(&buf, n * 4)); CK(cudaMemset(buf, 0, n * 4));
     for (int reps : {1, 8}) {
