@@ -52,7 +52,7 @@ class CrossBwdParams(C.Structure):
 
 
 EXPORTS = ("ss2d_abi_version", "ss2d_build_info", "ss2d_error_string", "ss2d_scan_ckpt_floats", "ss2d_cross_work_floats",
-           "ss2d_scan_family", "ss2d_set_default_family", "ss2d_cross_family",
+           "ss2d_scan_family", "ss2d_set_default_family", "ss2d_cross_family", "ss2d_optim_partials", "ss2d_optim_clip_adam",
            "ss2d_plane_transpose", "ss2d_selective_scan_fwd",
            "ss2d_selective_scan_bwd", "ss2d_cross_scan", "ss2d_cross_merge", "ss2d_cross_scan_fwd",
            "ss2d_cross_scan_bwd", "ss2d_dwconv_silu_fwd", "ss2d_dwconv_silu_bwd", "ss2d_merge_norm_gate_fwd",
@@ -84,6 +84,11 @@ def lib():
         L.ss2d_set_default_family.argtypes = [C.c_int]
         L.ss2d_cross_family.restype = C.c_int
         L.ss2d_cross_family.argtypes = [_i64, _i64, _i64, _i64, _i64, _i32, _i32]
+        L.ss2d_optim_partials.restype = _i64
+        L.ss2d_optim_partials.argtypes = []
+        _f = C.c_float
+        L.ss2d_optim_clip_adam.restype = C.c_int
+        L.ss2d_optim_clip_adam.argtypes = [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _f, _f, _f, _f, _i64, _f, _f, _vp]
         sigs = {n: [_vp, _vp] for n in ("ss2d_selective_scan_fwd", "ss2d_selective_scan_bwd", "ss2d_cross_scan_fwd",
                                         "ss2d_cross_scan_bwd")}
         sigs.update({n: [_vp, _vp, _i64, _i64, _i64, _i64, _i32, _vp] for n in ("ss2d_cross_scan", "ss2d_cross_merge")})

@@ -228,6 +228,21 @@ int ss2d_merge_norm_gate_bwd(const float *y, const float *weight, const float *b
                              int64_t z_pstride, const float *dout, float *dy, float *dz, int64_t dz_pstride,
                              float *dweight, float *dbias, int64_t batch, int64_t D, int64_t L, void *stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * optimizer side of the data-parallel training step: global-norm clip + Adam + zero-grad over ONE
+ * flat fp32 bucket, two launches.  Replaces clip_grad_norm_(params, 0.001); optimizer.step(); optimizer.zero_grad()
+ * of ITS/train.py:61,89-91 (Adam(lr, betas=(0.9, 0.999), eps=1e-8), train.py:16).
+ *   param, grad, exp_avg, exp_avg_sq : n f32 each, 16-byte aligned; grad holds the all-reduce SUM over ranks and is ZEROED
+ *   on return; grad_scale = 1 / world size; partials: SS2D_OPTIM_PARTIALS f32 scratch; norm_out: NULL or 1 f32 that
+ *   receives the total norm of the averaged gradient (what clip_grad_norm_ returns); step >= 1 (bias correction);
+ *   max_norm <= 0 disables clipping.
+ * ------------------------------------------------------------------------------------------- */
+#define SS2D_OPTIM_PARTIALS 592
+int64_t ss2d_optim_partials(void);
+int ss2d_optim_clip_adam(float *param, float *grad, float *exp_avg, float *exp_avg_sq, int64_t n, float *partials,
+                         float *norm_out, float lr, float beta1, float beta2, float eps, int64_t step, float max_norm,
+                         float grad_scale, void *stream);
+
 #ifdef __cplusplus
 }
 #endif
