@@ -172,6 +172,7 @@ def main():
     ap.add_argument("--dtype", default="fp32", choices=["fp32", "bf16"])
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-model", action="store_true", help="skip the model-level legs (train / infer / config-1 CPU forward)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -254,7 +255,8 @@ def main():
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    dom, dom_ms, dom_bytes = ("sl_bwd_kernel", bwd_ms, bb) if bwd_ms >= fwd_ms else ("sl_fwd_kernel", fwd_ms, fb)
+    fam = "sl" if ckpt.family == _lib.FAMILY_STATELANES else "scan"  # kernel family that served this shape
+    dom, dom_ms, dom_bytes = (f"{fam}_bwd_kernel", bwd_ms, bb) if bwd_ms >= fwd_ms else (f"{fam}_fwd_kernel", fwd_ms, fb)
     achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650 (B200_PROFILING.md)",
@@ -268,7 +270,9 @@ def main():
     traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(traffic_file):
         try:
-            roofline["traffic"] = json.load(open(traffic_file)).get(f"{dom}_{args.dtype}")
+            tj = json.load(open(traffic_file))
+            roofline["traffic"] = tj.get(f"{dom}_{args.dtype}")
+            roofline["traffic_source"] = tj.get("_capture")
         except Exception:
             pass
 
@@ -276,7 +280,9 @@ def main():
     host = make_inputs("cpu", dtype, seed=rank, pin=True)
     names = ("u", "delta", "A", "B", "C", "D", "delta_bias", "dout")
     h2d = sum(host[k].numel() * host[k].element_size() for k in names)
-    res_host = torch.empty(WORK["dim"] * (WORK["dstate"] + 2) + 1, dtype=torch.float32).pin_memory()
+    # the step's results: out, du, ddelta, dB, dC, dA, dD, ddelta_bias — all of them go back to pinned host memory
+    res_names = ("out", "du", "ddelta", "dA", "dB", "dC", "dD", "ddelta_bias")
+    res_host = []
 
     # two device input sets: the H2D copy of step i+1 (copy stream) overlaps the kernels of step i (compute stream);
     # every step still copies all of its inputs from pinned host memory and reads its result back
@@ -300,8 +306,11 @@ def main():
             o, xx, ck, _ = scan_fwd(*a, True, 1, True)
             g = scan_bwd(*a, dd["dout"], xx, True, 1, ckpt=ck)
             freed[slot].record(comp_stream)
-            res = torch.cat([g[2].flatten(), g[5], g[6], o.sum().view(1)])  # dA, dD, ddelta_bias, checksum(out)
-            res_host.copy_(res, non_blocking=True)
+            res = (o,) + tuple(g[:7])
+            if not res_host:
+                res_host.extend(torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in res)
+            for h, t in zip(res_host, res):
+                h.copy_(t, non_blocking=True)
 
     def e2e_run(n):
         copy_in(0)
@@ -323,7 +332,85 @@ def main():
     e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps  # host clock around a fully synchronised region
     e2e_ms = max_over_ranks(e2e_ms, dev)
     e2e = {"value": (fb + bb) * world / (e2e_ms * 1e-3) / 1e9, "unit": "GB/s", "ms_per_step": e2e_ms,
-           "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": res_host.numel() * 4}
+           "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": sum(t.numel() * t.element_size() for t in res_host),
+           "d2h": "out, du, ddelta, dA, dB, dC, dD, ddelta_bias (every result tensor of the step)"}
+
+    # ---- secondary measurements (explain the headline; same device, CUDA events) ----
+    def micro_other(dt2):
+        """The same microbench with 16-bit inputs (fp32 state and output): fwd / bwd launch times and roofline fraction."""
+        d2 = make_inputs(dev, dt2, seed=rank)
+        a2 = (d2["u"], d2["delta"], d2["A"], d2["B"], d2["C"], d2["D"], d2["delta_bias"])
+        o2, x2, ck2, _ = scan_fwd(*a2, True, 1, True)
+        f_ms, _ = kernel_ms(lambda: scan_fwd(*a2, True, 1, True), n_k)
+        b_ms, _ = kernel_ms(lambda: scan_bwd(*a2, d2["dout"], x2, True, 1, ckpt=ck2), n_k)
+        f2, b2 = algorithmic_bytes(WORK["batch"], WORK["dim"], WORK["dstate"], WORK["seqlen"], WORK["ngroups"], 2, 4)
+        return {"fwd_ms": f_ms, "bwd_ms": b_ms, "algorithmic_MB": (f2 + b2) / 1e6, "GBps": (f2 + b2) / (f_ms + b_ms) / 1e6,
+                "fwd_bwd_frac": (f2 + b2) / (f_ms + b_ms) / 1e6 / peak, "dtype": "bf16 in / f32 state+out"}
+
+    def micro_fused():
+        """Seam S3 at the microbench shape: CrossScan + scan + CrossMerge as ONE op (no 4x copies), fwd and fwd+bwd through
+        autograd, against SURVEY §8d's Level-B bytes (fwd 167.8 MB, bwd 310.4 MB fp32)."""
+        from focalnet_b200 import CrossMerge, CrossScan, FusedCrossScanFn, SelectiveScanOflex
+        B, D, Hh, Ww, N = WORK["batch"], WORK["dim"] // 4, 64, 64, WORK["dstate"]
+        Ln = Hh * Ww
+        g = torch.Generator().manual_seed(7)
+        xs = torch.randn(B, D, Hh, Ww, generator=g).to(dev).requires_grad_()
+        leaves = [xs] + [t.detach().clone().requires_grad_() for t in (d["delta"].float(), d["A"], d["B"].float(), d["C"].float(),
+                                                                      d["D"], d["delta_bias"])]
+        dy = torch.randn(B, D, Ln, generator=g).to(dev)
+
+        def fused(bwd):
+            y = FusedCrossScanFn.apply(*leaves, True)
+            if bwd:
+                y.backward(dy)
+
+        def unfused(bwd):
+            u4 = CrossScan.apply(leaves[0]).view(B, 4 * D, Ln)
+            ys = SelectiveScanOflex.apply(u4, *leaves[1:], True, 1, 1, True)
+            y = CrossMerge.apply(ys.view(B, 4, D, Hh, Ww))
+            if bwd:
+                y.backward(dy)
+
+        s4 = 4
+        lvlB_f = s4 * (B * D * Ln + B * 4 * D * Ln + 2 * B * 4 * N * Ln) + s4 * B * D * Ln
+        lvlB_b = lvlB_f + s4 * (B * D * Ln + B * 4 * D * Ln + 2 * B * 4 * N * Ln)
+        r = {}
+        for name, fn in (("fused", fused), ("unfused", unfused)):
+            with torch.no_grad():
+                f_ms, _ = kernel_ms(lambda: fn(False), n_k)
+            fb_ms, _ = kernel_ms(lambda: fn(True), n_k)
+            r[name] = {"fwd_ms": f_ms, "fwd_bwd_ms": fb_ms}
+        r["levelB_MB"] = {"fwd": lvlB_f / 1e6, "fwd_bwd": (lvlB_f + lvlB_b) / 1e6}
+        r["fwd_bwd_frac_levelB"] = (lvlB_f + lvlB_b) / r["fused"]["fwd_bwd_ms"] / 1e6 / peak
+        r["fused_over_unfused"] = r["fused"]["fwd_bwd_ms"] / r["unfused"]["fwd_bwd_ms"]
+        r["note"] = "through autograd incl. zero fills; unfused = this library's cross_scan + S1 scan + cross_merge kernels"
+        return r
+
+    extra = {}
+    if dtype == torch.float32:
+        for key, fn in (("bf16", lambda: micro_other(torch.bfloat16)), ("fused", micro_fused)):
+            try:
+                extra[key] = fn()
+            except Exception as exc:  # secondary legs never take the headline down
+                extra[key] = {"error": repr(exc)[:200]}
+        torch.cuda.empty_cache()
+    if not args.no_model and dtype == torch.float32:
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import model_legs
+        m_steps = max(5, min(args.steps, 20))
+        for key, leg in (("train", model_legs.train_leg), ("infer", model_legs.infer_leg)):
+            try:
+                extra[key] = leg(dev, rank, world, m_steps, 3, barrier, max_over_ranks)
+            except Exception as exc:
+                extra[key] = {"error": repr(exc)[:300]}
+                if world > 1:
+                    raise  # a rank that dropped out of a collective must not leave the others hanging
+            torch.cuda.empty_cache()
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                extra["model_cpu"] = model_legs.cpu_forward_leg(256)
+            except Exception as exc:
+                extra["model_cpu"] = {"error": repr(exc)[:200]}
 
     if rank == 0:
         line = {"metric": "ss2d_scan_fwd_bwd_algorithmic_GBps", "value": value, "unit": "GB/s", "n_gpus": world,
@@ -334,7 +421,7 @@ def main():
                            "l2": "inputs (0.42 GB fp32) larger than the 126 MB L2; no flush", "seam": "S1 fwd+bwd",
                            "algorithmic_MB": (fb + bb) / 1e6},
                 "hbm_frac": value / world / peak, "roofline": roofline, "e2e": e2e, "gpu_launches": n_launch,
-                "clocks": clocks, "lib": _lib.lib().ss2d_build_info().decode()}
+                "clocks": clocks, "lib": _lib.lib().ss2d_build_info().decode(), **extra}
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = {k: v for k, v in cpu_baseline(args.dtype).items() if k != "seconds"}
             try:
