@@ -5,6 +5,28 @@
 #define SS2D_STR_(x) #x
 #define SS2D_STR(x) SS2D_STR_(x)
 
+#include <map>
+#include <mutex>
+#include <utility>
+
+namespace ss2d {
+int smem_optin_impl(const void *kern, int bytes) {
+    static std::mutex mu;
+    static std::map<std::pair<const void *, int>, int> done;  // (kernel, device) -> bytes already opted in
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return (int)e;
+    std::lock_guard<std::mutex> lock(mu);
+    int &have = done[{kern, dev}];
+    if (bytes > have) {
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+        if (e != cudaSuccess) return (int)e;
+        have = bytes;
+    }
+    return 0;
+}
+}  // namespace ss2d
+
 extern "C" int ss2d_abi_version(void) { return SS2D_ABI_VERSION; }
 
 extern "C" const char *ss2d_build_info(void) {

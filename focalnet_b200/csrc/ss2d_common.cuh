@@ -369,21 +369,11 @@ __device__ __forceinline__ void shift_down1(float P, float H, float &Pe, float &
         : "f"(H), "f"(P));
 }
 
-// Dynamic shared memory opt-in, raised at most once per (kernel instantiation, device, size): cudaFuncSetAttribute is a
-// driver round trip that has no business on every launch.  One static per instantiation of this template == per kernel.
-template <typename K> static inline int smem_optin(K kern, int bytes) {
-    static int done_dev = -1, done_bytes = 0;
-    int dev = 0;
-    cudaError_t e = cudaGetDevice(&dev);
-    if (e != cudaSuccess) return (int)e;
-    if (done_dev != dev || bytes > done_bytes) {
-        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-        if (e != cudaSuccess) return (int)e;
-        done_dev = dev;
-        done_bytes = bytes;
-    }
-    return 0;
-}
+// Dynamic shared memory opt-in, raised at most once per (kernel, device, size): cudaFuncSetAttribute is a driver round trip
+// that has no business on every launch.  Keyed by the kernel's ADDRESS (kernels of equal signature share the pointer TYPE,
+// so a static per template instantiation would be shared between them).
+int smem_optin_impl(const void *kern, int bytes);
+template <typename K> static inline int smem_optin(K kern, int bytes) { return smem_optin_impl(reinterpret_cast<const void *>(kern), bytes); }
 
 }  // namespace ss2d
 
