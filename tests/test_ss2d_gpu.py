@@ -1,6 +1,7 @@
 """GPU parity of CrossScan/CrossMerge (S2), the fused SS2D core (S3), the dwconv+SiLU pre-mix and the drop-in
 modules.  Checkers: golden vectors produced by the Python reference (tests/golden), the C oracle, and — for the
 fused core at model shapes — the unfused composition of this library's own S1/S2 kernels."""
+import functools
 import os
 import sys
 
@@ -251,6 +252,9 @@ def test_ss2d_forward_on_reference_shaped_module():
             self.out_norm = torch.nn.LayerNorm(D)
             self.out_proj = torch.nn.Linear(D, dm, bias=False)
             self.dropout = torch.nn.Identity()
+            # the configuration attributes of the shipped (forward type v4) module that block_supported() inspects
+            self.d_conv, self.disable_z, self.disable_z_act, self.out_norm_shape, self.act = 3, False, False, "v0", torch.nn.SiLU()
+            self.forward_core = functools.partial(lambda *a, **k: None, force_fp32=False, no_einsum=True)
 
     m = M().cuda()
     x = torch.randn(2, 9, 11, dm).cuda()
