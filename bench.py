@@ -362,14 +362,14 @@ def main():
         def fused(bwd):
             y = FusedCrossScanFn.apply(*leaves, True)
             if bwd:
-                y.backward(dy)
+                torch.autograd.grad(y, leaves, dy)  # (not .backward(): no accumulate-into-.grad kernels in the timing)
 
         def unfused(bwd):
             u4 = CrossScan.apply(leaves[0]).view(B, 4 * D, Ln)
             ys = SelectiveScanOflex.apply(u4, *leaves[1:], True, 1, 1, True)
             y = CrossMerge.apply(ys.view(B, 4, D, Hh, Ww))
             if bwd:
-                y.backward(dy)
+                torch.autograd.grad(y, leaves, dy)
 
         s4 = 4
         lvlB_f = s4 * (B * D * Ln + B * 4 * D * Ln + 2 * B * 4 * N * Ln) + s4 * B * D * Ln

@@ -183,7 +183,7 @@ scan_fwd_kernel(const ss2d_scan_fwd_params p, const int tiles_per_group, const F
             __syncwarp();
             if (active) {
                 if constexpr (CROSS) {
-                    red_block_cross<T>(reinterpret_cast<float *>(o_row), y, g, tl, L, xinfo, fl.vec_out);
+                    if (o_row) red_block_cross<T>(reinterpret_cast<float *>(o_row), y, g, tl, L, xinfo, fl.vec_out);
                 } else if (o_row) {
                     store_block<out_t, T>(o_row + tl, y, valid, fl.vec_out);
                     if (z_row) {
@@ -281,7 +281,8 @@ extern "C" int ss2d_selective_scan_fwd(const ss2d_scan_fwd_params *pp, void *str
 extern "C" int ss2d_cross_scan_fwd(const ss2d_cross_fwd_params *pp, void *stream) {
     if (!pp) return SS2D_EINVAL;
     const ss2d_cross_fwd_params &c = *pp;
-    if (!c.x || !c.delta || !c.B || !c.C || !c.A || !c.y) return SS2D_EINVAL;
+    if (!c.x || !c.delta || !c.B || !c.C || !c.A) return SS2D_EINVAL;
+    if (!c.y && !c.ckpt) return SS2D_EINVAL;  // y == NULL: states-only sweep that rebuilds ckpt for the backward
     if (c.batch <= 0 || c.D <= 0 || c.H <= 0 || c.W <= 0 || c.dstate <= 0 || c.dstate > SS2D_MAX_DSTATE) return SS2D_EINVAL;
     if (c.H * c.W > 0x7fffffffLL || c.batch * 4 * c.D > 0x7fffffffLL) return SS2D_EINVAL;
     const int64_t L = c.H * c.W;
@@ -303,6 +304,7 @@ extern "C" int ss2d_cross_scan_fwd(const ss2d_cross_fwd_params *pp, void *stream
         float *xT = c.work, *yT = c.work + n;
         int rc = ss2d::plane_transpose(reinterpret_cast<const float *>(c.x), xT, c.batch * c.D, (int)c.H, (int)c.W, false, s);
         if (rc != 0) return rc;
+        if (!c.y) return ss2d::sl::launch_cross_fwd(p, ss2d::sl::CrossAux{xT, nullptr, nullptr}, s);
         cudaError_t e = cudaMemsetAsync(yT, 0, (size_t)n * sizeof(float), s);
         if (e != cudaSuccess) return (int)e;
         rc = ss2d::sl::launch_cross_fwd(p, ss2d::sl::CrossAux{xT, nullptr, yT}, s);
@@ -312,7 +314,7 @@ extern "C" int ss2d_cross_scan_fwd(const ss2d_cross_fwd_params *pp, void *stream
     // warp-scan kernels: all four directions accumulate into y.  One launch (sum in arrival order), or — deterministic — one
     // launch per direction in the order k = 0, 1, 2, 3 (every y element then receives its four terms in that order).
     // The state-lanes branch above is bit-reproducible as it stands: y and y^T each take exactly two commutative adds onto 0.
-    if (!c.deterministic)
+    if (!c.deterministic || !c.y)
         return ss2d::dispatch_fwd<true>(p, reinterpret_cast<cudaStream_t>(stream), ss2d::CrossInfo{(int)c.H, (int)c.W, -1});
     for (int k = 0; k < 4; ++k) {
         const int rc = ss2d::dispatch_fwd<true>(p, reinterpret_cast<cudaStream_t>(stream), ss2d::CrossInfo{(int)c.H, (int)c.W, k});

@@ -189,7 +189,7 @@ __device__ __forceinline__ void sl_fwd_body(const ss2d_scan_fwd_params &p, const
         for (int i = 0; i < OWN; ++i) o[i] = fmaf(Dv, uv[i], o[i]);
         const int t_own = blk * BK + OWN * ng;
         if constexpr (CROSS) {
-            if (store) red_own_cross<OWN>(reinterpret_cast<float *>(o_row), ywalk, o);
+            if (store && o_row) red_own_cross<OWN>(reinterpret_cast<float *>(o_row), ywalk, o);
             ywalk.advance(BK);
         } else if constexpr (FAST) {
             if (store && o_row) stg_k<out_t, OWN>(o_row + t_own, o, OWN, true);
@@ -408,7 +408,7 @@ bool cross_covered(const ss2d_scan_fwd_params &p) {
 }
 
 int launch_cross_fwd(const ss2d_scan_fwd_params &p, const CrossAux &xi, cudaStream_t s) {
-    if (!aligned16(xi.uT) || !aligned16(xi.accT)) return SS2D_ESTRIDE;
+    if (!aligned16(xi.uT) || (xi.accT && !aligned16(xi.accT))) return SS2D_ESTRIDE;
     return states_per_lane(p) == 4 ? launch_fwd_t<float, float, 4, 4, 32, true>(p, s, xi) : launch_fwd_t<float, float, 2, 4, 64, true>(p, s, xi);
 }
 

@@ -131,7 +131,11 @@ class SelectiveScanCore(_SelectiveScanBase):
 # --------------------------------------------------------------------------------------------- S3
 class FusedCrossScanFn(torch.autograd.Function):
     """x (B,D,H,W) spatial, delta (B,4D,L) / Bs, Cs (B,4,N,L) in scan order  ->  y (B,D,L) spatial fp32 =
-    CrossMerge(selective_scan(CrossScan(x), ...)) without the 4x copies (ss2d_cross_scan_fwd/_bwd)."""
+    CrossMerge(selective_scan(CrossScan(x), ...)) without the 4x copies (ss2d_cross_scan_fwd/_bwd).
+
+    ``FusedCrossScanFn.recompute = True`` trades one extra states-only forward sweep in the backward for not keeping the
+    block-boundary states between the passes (activation memory of the scan drops to the inputs autograd holds anyway)."""
+    recompute = False
 
     @staticmethod
     def forward(ctx, x, delta, A, Bs, Cs, Ds, delta_bias, delta_softplus=True, deterministic=False):
@@ -147,10 +151,14 @@ class FusedCrossScanFn(torch.autograd.Function):
         Ds = None if Ds is None else Ds.contiguous().float()
         delta_bias = None if delta_bias is None else delta_bias.contiguous().float()
         y = torch.zeros((B, D, L), device=x.device, dtype=torch.float32)
-        ckpt = torch.empty(_n_ckpt(B, 4 * D, L, N), device=x.device, dtype=torch.float32)
+        # block-boundary states for the backward: not written at all when nothing needs a gradient (inference), nor in
+        # `recompute` mode, where the backward rebuilds them with a states-only sweep instead of keeping them alive
+        # between the two passes (as many bytes as delta: 1.6 GB per call at B=32, L=16384)
+        keep = any(ctx.needs_input_grad) and not FusedCrossScanFn.recompute
+        ckpt = torch.empty(_n_ckpt(B, 4 * D, L, N), device=x.device, dtype=torch.float32) if keep else None
         P = _lib.CrossFwdParams()
         FusedCrossScanFn._fill(P, x, delta, A, Bs, Cs, Ds, delta_bias, delta_softplus, (B, D, H, W, N))
-        P.y, P.ckpt = y.data_ptr(), ckpt.data_ptr()
+        P.y, P.ckpt = y.data_ptr(), _ptr(ckpt)
         # the family is resolved ONCE here and handed to the backward (the checkpoint layouts of the families differ)
         P.family = family = int(_lib.lib().ss2d_cross_family(B, D, H, W, N, _DT[x.dtype], 0))
         P.deterministic = int(bool(deterministic))
@@ -184,13 +192,26 @@ class FusedCrossScanFn(torch.autograd.Function):
         B, D, H, W = x.shape
         L, N = H * W, A.shape[1]
         dy = dy.contiguous().float()
-        dx = torch.zeros((B, D, L), device=x.device, dtype=torch.float32)
+        if ckpt is None:  # recompute mode: states-only forward sweep (y = NULL) into a transient buffer
+            ckpt = torch.empty(_n_ckpt(B, 4 * D, L, N), device=x.device, dtype=torch.float32)
+            Pf = _lib.CrossFwdParams()
+            FusedCrossScanFn._fill(Pf, x, delta, A, Bs, Cs, Ds, delta_bias, ctx.delta_softplus, (B, D, H, W, N))
+            Pf.y, Pf.ckpt, Pf.family = None, ckpt.data_ptr(), ctx.family
+            wf = FusedCrossScanFn._work(x, N, L, False, ctx.family)
+            Pf.work = _ptr(wf)
+            with torch.cuda.device(x.device):
+                _lib.check(_lib.lib().ss2d_cross_scan_fwd(C_byref(Pf), _stream(x)), "ss2d_cross_scan_fwd (states only)")
+        # every accumulator the kernels add into comes out of ONE zero-filled buffer (one fill launch instead of six);
+        # pieces start on 16-byte boundaries (the kernels use 128-bit reductions)
+        sizes = [B * D * L, A.numel(), B * 4 * N * L, B * 4 * N * L, 4 * D if Ds is not None else 0, 4 * D if delta_bias is not None else 0]
+        offs, tot = [], 0
+        for n in sizes:
+            offs.append(tot)
+            tot += (n + 3) // 4 * 4
+        acc = torch.zeros(tot, device=x.device, dtype=torch.float32)
+        dx, dA, dB, dC, dDs, dbias = (acc[o:o + n] if n else None for o, n in zip(offs, sizes))
+        dx, dA, dB, dC = dx.view(B, D, L), dA.view_as(A), dB.view(B, 4, N, L), dC.view(B, 4, N, L)
         ddelta = torch.empty_like(delta)
-        dA = torch.zeros_like(A)
-        dB = torch.zeros((B, 4, N, L), device=x.device, dtype=torch.float32)
-        dC = torch.zeros_like(dB)
-        dDs = torch.zeros_like(Ds) if Ds is not None else None
-        dbias = torch.zeros_like(delta_bias) if delta_bias is not None else None
         P = _lib.CrossBwdParams()
         FusedCrossScanFn._fill(P.f, x, delta, A, Bs, Cs, Ds, delta_bias, ctx.delta_softplus, (B, D, H, W, N))
         P.f.ckpt, P.f.family, P.f.deterministic = ckpt.data_ptr(), ctx.family, int(ctx.deterministic)

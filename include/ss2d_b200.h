@@ -148,7 +148,9 @@ int ss2d_cross_permute(const void *src, void *dst, int64_t B, int64_t C, int64_t
  *   A (4*D,dstate), Dskip (4*D), delta_bias (4*D) : f32, channel index k*D+d (vmamba_layers.py:273-279)
  *   y      : (batch, D, H*W) f32, SPATIAL order, = CrossMerge of the four scans; MUST BE ZEROED by the caller
  *            (each direction accumulates with red.global.add.f32, so the sum order is not deterministic)
- *   ckpt   : ss2d_scan_ckpt_floats(batch, 4*D, H*W, dstate) f32 elements, consumed by the backward
+ *            y == NULL with ckpt != NULL: states-only sweep (rebuilds ckpt for a backward that did not keep it)
+ *   ckpt   : ss2d_scan_ckpt_floats(batch, 4*D, H*W, dstate) f32 elements, consumed by the backward; NULL: not written
+ *            (inference)
  * ------------------------------------------------------------------------------------------- */
 typedef struct ss2d_cross_fwd_params {
     int64_t batch, D, H, W, dstate;

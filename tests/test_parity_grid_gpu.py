@@ -128,3 +128,37 @@ def test_fused_core_fwd_bwd_matches_oracle_composition(shape, family, determinis
     assert rel_err(leaves[0].grad.reshape(B, D, L), dx_ref) < 1e-3, "dx"
     for leaf, k in zip(leaves[1:], ("ddelta", "dA", "dB", "dC", "dD", "ddelta_bias")):
         assert rel_err(leaf.grad, b[k]) < 1e-3, k
+
+
+@pytest.mark.parametrize("family", ["statelanes", "warpscan"])
+def test_fused_core_recompute_mode_and_inference_without_checkpoints(family):
+    """`FusedCrossScanFn.recompute` (states rebuilt in the backward instead of kept) gives the gradients of the default
+    mode; a no-grad forward (no checkpoint buffer at all) gives the same y."""
+    from focalnet_b200 import FusedCrossScanFn, _lib
+    B, D, H, W, N = 2, 48, 32, 48, 16
+    L = H * W
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(B, D, H, W, generator=g).cuda()
+    delta = (0.5 * torch.rand(B, 4 * D, L, generator=g)).cuda()
+    A = (-0.5 * torch.rand(4 * D, N, generator=g)).cuda()
+    Bs, Cs = torch.randn(B, 4, N, L, generator=g).cuda(), torch.randn(B, 4, N, L, generator=g).cuda()
+    Ds, bias = torch.randn(4 * D, generator=g).cuda(), (0.5 * torch.rand(4 * D, generator=g)).cuda()
+    dy = torch.randn(B, D, L, generator=g).cuda()
+    fam = {"statelanes": _lib.FAMILY_STATELANES, "warpscan": _lib.FAMILY_WARPSCAN}[family]
+    old = _lib.lib().ss2d_set_default_family(fam)
+    try:
+        res = []
+        for rec in (False, True):
+            FusedCrossScanFn.recompute = rec
+            leaves = [t.clone().requires_grad_() for t in (x, delta, A, Bs, Cs, Ds, bias)]
+            y = FusedCrossScanFn.apply(*leaves, True)
+            y.backward(dy)
+            res.append((y.detach(), [t.grad for t in leaves]))
+        with torch.no_grad():
+            y_inf = FusedCrossScanFn.apply(x, delta, A, Bs, Cs, Ds, bias, True)
+    finally:
+        FusedCrossScanFn.recompute = False
+        _lib.lib().ss2d_set_default_family(old)
+    assert rel_err(res[1][0], res[0][0]) < 1e-6 and rel_err(y_inf, res[0][0]) < 1e-6
+    for a, b, k in zip(res[1][1], res[0][1], ("dx", "ddelta", "dA", "dB", "dC", "dD", "dbias")):
+        assert rel_err(a, b) < 1e-5, k
