@@ -77,6 +77,14 @@ template <typename T, int K> __device__ __forceinline__ void lds_k(const T *p, f
         }
     }
 }
+// a lane's OWN (2 or 4) consecutive steps starting at the even / multiple-of-4 step offset `s0` of a tile row; `mirrored`
+// rows keep step e at offset e ^ 3 (16-byte pieces copied from a sequence that runs backwards in memory)
+template <typename T, int K> __device__ __forceinline__ void lds_own(const T *row, int s0, bool mirrored, float (&v)[K]) {
+    float t[K];
+    lds_k<T, K>(row + ((mirrored && K == 2) ? (s0 ^ 2) : s0), t);  // selects, not branches: the callers' loops stay one basic block
+#pragma unroll
+    for (int i = 0; i < K; ++i) v[i] = mirrored ? t[K - 1 - i] : t[i];
+}
 // K consecutive elements global <-> registers; `valid` = how many lie inside the sequence (<= 0: none)
 template <typename T, int K> __device__ __forceinline__ void ldg_k(const T *p, float (&v)[K], int valid, bool vec) {
     if (vec && valid >= K) {
@@ -154,12 +162,20 @@ template <typename T, int TT, int NT> struct RowStager {
                 d += dst_step;
             }
         } else {
-            T *out = reinterpret_cast<T *>(reinterpret_cast<unsigned char *>(sdst) + buf_off);
-            for (int idx = threadIdx.x; idx < nrows_valid * TT; idx += NT) {
-                const int r = idx / TT, e = idx % TT;
-                const int row = perm_sn ? (r % perm_sn) * (kN / perm_sn) + r / perm_sn : r;
-                out[row * rs + e] = t0 + e < L ? base[(int64_t)r * rstride + t0 + e] : from_f32<T>(0.f);
-            }
+            issue_elems(t0, L, buf_off, 0);
+        }
+    }
+    // element-wise, bounds-checked fill of one stage (unaligned tensors; the short last stage of the fused seam).
+    // mirror_L > 0: scan step l is element mirror_L-1-l of the row and step e of the tile is kept at offset e ^ 3 — the
+    // layout CopyList::add(mirror_L) produces for the full stages
+    __device__ __forceinline__ void issue_elems(int t0, int L, int buf_off, int mirror_L) const {
+        T *out = reinterpret_cast<T *>(reinterpret_cast<unsigned char *>(sdst) + buf_off);
+        for (int idx = threadIdx.x; idx < nrows_valid * TT; idx += NT) {
+            const int r = idx / TT, e = idx % TT;
+            const int row = perm_sn ? (r % perm_sn) * (kN / perm_sn) + r / perm_sn : r;
+            const int l = t0 + e;
+            const int64_t src_e = mirror_L > 0 ? mirror_L - 1 - l : l;
+            out[row * rs + (mirror_L > 0 ? (e ^ 3) : e)] = l < L ? base[(int64_t)r * rstride + src_e] : from_f32<T>(0.f);
         }
     }
 };
@@ -178,10 +194,13 @@ template <int NT, int NCOPY> struct CopyList {
 #pragma unroll
         for (int j = 0; j < NCOPY; ++j) { src[j] = nullptr; dst[j] = 0; adv[j] = 0; }
     }
-    // rows x TTs steps of `g` (row stride g_rstride), first stage at step t_first, following stages stage_step steps on
+    // rows x TTs steps of `g` (row stride g_rstride), first stage at step t_first, following stages stage_step steps on.
+    // mirror_L > 0 (fused seam, directions 2 / 3): scan step l is element mirror_L-1-l of the row.  The stage's elements are
+    // still copied as ascending 16-byte pieces, the piece that holds steps 4m..4m+3 lands at tile offset 4m with its four
+    // values in descending step order — step e of the tile lives at offset e ^ 3 (readers un-mirror, see lds_own)
     template <typename T>
     __device__ __forceinline__ void add(T *smem_rows, int rs_elems, const T *g, int64_t g_rstride, int nrows, int rows_valid, int TTs,
-                                        int perm_sn, int t_first, int stage_step) {
+                                        int perm_sn, int t_first, int stage_step, int mirror_L = 0) {
         constexpr int per = 16 / (int)sizeof(T);
         const int PPR = TTs / per;
 #pragma unroll
@@ -191,9 +210,15 @@ template <int NT, int NCOPY> struct CopyList {
                 const int r = local / PPR, q = local % PPR;
                 if (r < rows_valid) {
                     const int row = perm_sn ? (r % perm_sn) * (kN / perm_sn) + r / perm_sn : r;
-                    src[j] = reinterpret_cast<const unsigned char *>(g + (int64_t)r * g_rstride + q * per + t_first);
-                    dst[j] = smem_u32(smem_rows + row * rs_elems + q * per);
-                    adv[j] = stage_step * (int)sizeof(T);
+                    if (mirror_L > 0) {
+                        src[j] = reinterpret_cast<const unsigned char *>(g + (int64_t)r * g_rstride + (mirror_L - t_first - TTs) + q * per);
+                        dst[j] = smem_u32(smem_rows + row * rs_elems + (TTs - per - q * per));
+                        adv[j] = -stage_step * (int)sizeof(T);
+                    } else {
+                        src[j] = reinterpret_cast<const unsigned char *>(g + (int64_t)r * g_rstride + q * per + t_first);
+                        dst[j] = smem_u32(smem_rows + row * rs_elems + q * per);
+                        adv[j] = stage_step * (int)sizeof(T);
+                    }
                 }
             }
         }
@@ -232,45 +257,6 @@ struct DirWalk {
         }
     }
     __device__ __forceinline__ int off() const { return (k & 1) ? h * W + w : lin; }
-};
-
-// Element-wise (4-byte cp.async) gather of `u` / `dout` rows from spatial-order fp32 planes into a tile in SCAN
-// order.  A thread owns one step position e of the tile and rows r0, r0+RSTEP, ...: one DirWalk per thread.
-template <int NT, int TTs, int NROW> struct GatherList {
-    static_assert(NT % TTs == 0, "threads must tile the steps of a stage");
-    static constexpr int RSTEP = NT / TTs;
-    static constexpr int NG = (NROW + RSTEP - 1) / RSTEP;
-    const float *src;   // plane of row r0
-    int64_t row_step;   // elements between this thread's rows
-    uint32_t dst;       // shared address of (row r0, e) in ring slot 0
-    int dst_step, nrow, l;  // nrow: rows this thread copies; l: scan step of its element in the NEXT stage to issue
-    DirWalk walk;
-    __device__ __forceinline__ void init(float *smem_rows, int rs_elems, const float *plane0, int64_t plane_stride, int rows_valid, int k,
-                                         int H, int W, int L, int t_first) {
-        const int e = threadIdx.x % TTs, r0 = threadIdx.x / TTs;
-        src = plane0 + (int64_t)r0 * plane_stride;
-        row_step = (int64_t)RSTEP * plane_stride;
-        dst = smem_u32(smem_rows + r0 * rs_elems + e);
-        dst_step = RSTEP * rs_elems * 4;
-        nrow = r0 < rows_valid ? (rows_valid - r0 + RSTEP - 1) / RSTEP : 0;
-        l = t_first + e;
-        walk.init(k, H, W, L, l);
-    }
-    // copy this thread's element of every row for the stage it points at, then move `stage_step` steps on
-    __device__ __forceinline__ void issue(int slot_off, int L, int stage_step) {
-        if (l < L && l >= 0) {
-            const float *s = src + walk.off();
-            uint32_t d = dst + slot_off;
-#pragma unroll
-            for (int j = 0; j < NG; ++j) {
-                if (j < nrow) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(d), "l"(s) : "memory");
-                s += row_step;
-                d += dst_step;
-            }
-        }
-        l += stage_step;
-        walk.advance(stage_step);
-    }
 };
 
 // Accumulate OWN consecutive scan steps starting at `walk` into a spatial-order fp32 plane (CrossMerge / CrossScan^T

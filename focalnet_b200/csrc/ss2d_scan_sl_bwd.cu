@@ -110,30 +110,31 @@ sl_bwd_kernel(const ss2d_scan_bwd_params pb, const int tiles_per_group, const Fl
               p.C_nstride, kN, kN, fl.vec_bc, SN);
 
     // FAST: one flattened copy list instead of the five stagers
-    constexpr int NPIECE = CROSS ? (CPC + 2 * kN) * (BK * (int)sizeof(in_t) / 16)
-                                 : (2 * CPC + 2 * kN) * (BK * (int)sizeof(in_t) / 16) + CPC * (BK * (int)sizeof(out_t) / 16);
+    // (fused seam: u / dout rows are rows of x / dy, of their transposed copies, or the same rows walked backwards — the
+    // mirrored 16-byte pieces of CopyList::add, un-mirrored by lds_own; L % 16 == 0 there, so no stage is ever short)
+    constexpr int NPIECE = (2 * CPC + 2 * kN) * (BK * (int)sizeof(in_t) / 16) + CPC * (BK * (int)sizeof(out_t) / 16);
     constexpr int NCOPY = (NPIECE + NT - 1) / NT;
     CopyList<NT, NCOPY> cl;
-    GatherList<NT, BK, CPC> gu, gg;
-    if constexpr (CROSS) {
-        const int t_first = ((int)((p.seqlen + BK - 1) / BK) - 1) * BK;
-        gu.init(reinterpret_cast<float *>(smem + SM::u_off), SM::RSU,
-                ((g & 1) ? aux.uT : reinterpret_cast<const float *>(p.u)) + b * p.u_bstride + urow0 * p.u_dstride, p.u_dstride, rows_valid,
-                g & 2, 1, 1, (int)p.seqlen, t_first);
-        gg.init(reinterpret_cast<float *>(smem + SM::g_off), SM::RSG,
-                ((g & 1) ? aux.doutT : reinterpret_cast<const float *>(pb.dout)) + b * pb.dout_bstride + urow0 * pb.dout_dstride,
-                pb.dout_dstride, rows_valid, g & 2, 1, 1, (int)p.seqlen, t_first);
-    }
+    const bool rev = CROSS && (g & 2);
     if constexpr (FAST) {
         const int t_first = ((int)((p.seqlen + BK - 1) / BK) - 1) * BK;
+        const int mirror_L = rev ? (int)p.seqlen : 0;
         cl.clear();
-        if constexpr (!CROSS)
+        if constexpr (CROSS)
+            cl.add(reinterpret_cast<float *>(smem + SM::u_off), SM::RSU,
+                   ((g & 1) ? aux.uT : reinterpret_cast<const float *>(p.u)) + b * p.u_bstride + urow0 * p.u_dstride, p.u_dstride, CPC,
+                   rows_valid, BK, 0, t_first, -BK, mirror_L);
+        else
             cl.add(reinterpret_cast<in_t *>(smem + SM::u_off), SM::RSU, reinterpret_cast<const in_t *>(p.u) + b * p.u_bstride + row0 * p.u_dstride,
                    p.u_dstride, CPC, rows_valid, BK, 0, t_first, -BK);
         cl.add(reinterpret_cast<in_t *>(smem + SM::d_off), SM::RSU,
                reinterpret_cast<const in_t *>(p.delta) + b * p.delta_bstride + row0 * p.delta_dstride, p.delta_dstride, CPC, rows_valid, BK, 0,
                t_first, -BK);
-        if constexpr (!CROSS)
+        if constexpr (CROSS)
+            cl.add(reinterpret_cast<float *>(smem + SM::g_off), SM::RSG,
+                   ((g & 1) ? aux.doutT : reinterpret_cast<const float *>(pb.dout)) + b * pb.dout_bstride + urow0 * pb.dout_dstride,
+                   pb.dout_dstride, CPC, rows_valid, BK, 0, t_first, -BK, mirror_L);
+        else
             cl.add(reinterpret_cast<out_t *>(smem + SM::g_off), SM::RSG,
                    reinterpret_cast<const out_t *>(pb.dout) + b * pb.dout_bstride + row0 * pb.dout_dstride, pb.dout_dstride, CPC, rows_valid, BK, 0,
                    t_first, -BK);
@@ -191,7 +192,6 @@ sl_bwd_kernel(const ss2d_scan_bwd_params pb, const int tiles_per_group, const Fl
         if (k >= 0) {
             if constexpr (FAST) {
                 cl.issue(slot_off);
-                if constexpr (CROSS) { gu.issue(slot_off, L, -BK); gg.issue(slot_off, L, -BK); }
             } else {
                 const int t0 = k * BK;
                 st_u.issue(t0, L, slot_off);
@@ -214,13 +214,13 @@ sl_bwd_kernel(const ss2d_scan_bwd_params pb, const int tiles_per_group, const Fl
         return v;
     };
     // this lane's OWN steps of block k: softplus, delta*u, (gated) dout -> exchange buffer k & 1
-    const int own_u = (warp * CPW + cw) * SM::RSU + OWN * ng, own_g = (warp * CPW + cw) * SM::RSG + OWN * ng;
+    const int row_u = (warp * CPW + cw) * SM::RSU, row_g = (warp * CPW + cw) * SM::RSG, own_u = row_u + OWN * ng;
     auto prepare = [&](int k, int slot_off, int xoff, float (&uv)[OWN], float (&dl)[OWN], float (&gv)[OWN]) {
         const unsigned char *sbuf = smem + slot_off;
         float dv[OWN], du[OWN];
         lds_k<in_t, OWN>(reinterpret_cast<const in_t *>(sbuf + SM::d_off) + own_u, dv);
-        lds_k<in_t, OWN>(reinterpret_cast<const in_t *>(sbuf + SM::u_off) + own_u, uv);
-        lds_k<out_t, OWN>(reinterpret_cast<const out_t *>(sbuf + SM::g_off) + own_g, gv);
+        lds_own<in_t, OWN>(reinterpret_cast<const in_t *>(sbuf + SM::u_off) + row_u, OWN * ng, rev, uv);
+        lds_own<out_t, OWN>(reinterpret_cast<const out_t *>(sbuf + SM::g_off) + row_g, OWN * ng, rev, gv);
         const int t_own = k * BK + OWN * ng;
         const int valid = active ? L - t_own : 0;  // may be <= 0 or > OWN
         if (z_row && k >= 0) {  // out = pre * silu(z): dz and the gated upstream gradient

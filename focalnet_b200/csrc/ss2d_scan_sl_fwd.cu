@@ -81,20 +81,26 @@ __device__ __forceinline__ void sl_fwd_body(const ss2d_scan_fwd_params &p, const
     st_C.init(reinterpret_cast<in_t *>(smem + SM::C_off), SM::RSB, reinterpret_cast<const in_t *>(p.C) + b * p.C_bstride + g * p.C_gstride,
               p.C_nstride, kN, kN, fl.vec_bc, SN);
 
-    // FAST: one flattened copy list instead of the four stagers
-    constexpr int NPIECE = ((CROSS ? 1 : 2) * CPC + 2 * kN) * (TT * (int)sizeof(in_t) / 16);
+    // FAST: one flattened copy list instead of the four stagers.  Fused seam: the u rows are rows of x (direction 0), of
+    // x^T (1), or the same rows walked backwards (2 / 3: mirrored 16-byte pieces, un-mirrored by lds_own) — contiguous
+    // 16-byte copies in every direction; the element-wise gather only serves a short last stage (L % TT != 0)
+    constexpr int NPIECE = (2 * CPC + 2 * kN) * (TT * (int)sizeof(in_t) / 16);
     constexpr int NCOPY = (NPIECE + NT - 1) / NT;
     CopyList<NT, NCOPY> cl;
-    GatherList<NT, TT, CPC> gu;
-    if constexpr (CROSS)
-        gu.init(reinterpret_cast<float *>(smem + SM::u_off), SM::RSU,
-                ((g & 1) ? aux.uT : reinterpret_cast<const float *>(p.u)) + b * p.u_bstride + urow0 * p.u_dstride, p.u_dstride, rows_valid,
-                g & 2, 1, 1, (int)p.seqlen, 0);
-    if constexpr (FAST) {
+    const bool rev = CROSS && (g & 2);
+    if constexpr (CROSS) {
+        const float *plane = ((g & 1) ? aux.uT : reinterpret_cast<const float *>(p.u)) + b * p.u_bstride + urow0 * p.u_dstride;
+        st_u.init(reinterpret_cast<in_t *>(smem + SM::u_off), SM::RSU, reinterpret_cast<const in_t *>(plane), p.u_dstride, CPC, rows_valid,
+                  false, 0);  // short last stage only (element-wise, bounds-checked)
         cl.clear();
-        if constexpr (!CROSS)
+        cl.add(reinterpret_cast<float *>(smem + SM::u_off), SM::RSU, plane, p.u_dstride, CPC, rows_valid, TT, 0, 0, TT, rev ? (int)p.seqlen : 0);
+    }
+    if constexpr (FAST) {
+        if constexpr (!CROSS) {
+            cl.clear();
             cl.add(reinterpret_cast<in_t *>(smem + SM::u_off), SM::RSU, reinterpret_cast<const in_t *>(p.u) + b * p.u_bstride + row0 * p.u_dstride,
                    p.u_dstride, CPC, rows_valid, TT, 0, 0, TT);
+        }
         cl.add(reinterpret_cast<in_t *>(smem + SM::d_off), SM::RSU,
                reinterpret_cast<const in_t *>(p.delta) + b * p.delta_bstride + row0 * p.delta_dstride, p.delta_dstride, CPC, rows_valid, TT, 0, 0,
                TT);
@@ -139,10 +145,10 @@ __device__ __forceinline__ void sl_fwd_body(const ss2d_scan_fwd_params &p, const
             // off the tensor — copy it with the bounds-checked stagers instead
             if (t0 + TT <= L) cl.issue(off);
             else {
-                if constexpr (!CROSS) st_u.issue(t0, L, off);
+                if constexpr (CROSS) st_u.issue_elems(t0, L, off, rev ? L : 0);
+                else st_u.issue(t0, L, off);
                 st_d.issue(t0, L, off); st_B.issue(t0, L, off); st_C.issue(t0, L, off);
             }
-            if constexpr (CROSS) gu.issue(off, L, TT);
         } else {
             st_u.issue(t0, L, off);
             st_d.issue(t0, L, off);
@@ -152,11 +158,11 @@ __device__ __forceinline__ void sl_fwd_body(const ss2d_scan_fwd_params &p, const
         cp_async_commit();
     };
     // this lane's OWN steps of block `blk` (tile of stage `sbuf`, block kb inside it): softplus, delta*u -> exchange buffer
-    const int own_off = (warp * CPW + cw) * SM::RSU + OWN * ng;
+    const int own_row = (warp * CPW + cw) * SM::RSU, own_off = own_row + OWN * ng;
     auto prepare = [&](const unsigned char *sbuf, int kb, int blk, float (&uv)[OWN], float &dl_sum) {
         float dv[OWN], dl[OWN], du[OWN];
         lds_k<in_t, OWN>(reinterpret_cast<const in_t *>(sbuf + SM::d_off) + own_off + kb * BK, dv);
-        lds_k<in_t, OWN>(reinterpret_cast<const in_t *>(sbuf + SM::u_off) + own_off + kb * BK, uv);
+        lds_own<in_t, OWN>(reinterpret_cast<const in_t *>(sbuf + SM::u_off) + own_row, OWN * ng + kb * BK, rev, uv);
         const int valid = L - (blk * BK + OWN * ng);
         dl_sum = 0.f;
 #pragma unroll
