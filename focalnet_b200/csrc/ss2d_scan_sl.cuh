@@ -162,7 +162,12 @@ template <typename T, int TT, int NT> struct RowStager {
                 d += dst_step;
             }
         } else {
-            issue_elems(t0, L, buf_off, 0);
+            T *out = reinterpret_cast<T *>(reinterpret_cast<unsigned char *>(sdst) + buf_off);
+            for (int idx = threadIdx.x; idx < nrows_valid * TT; idx += NT) {
+                const int r = idx / TT, e = idx % TT;
+                const int row = perm_sn ? (r % perm_sn) * (kN / perm_sn) + r / perm_sn : r;
+                out[row * rs + e] = t0 + e < L ? base[(int64_t)r * rstride + t0 + e] : from_f32<T>(0.f);
+            }
         }
     }
     // element-wise, bounds-checked fill of one stage (unaligned tensors; the short last stage of the fused seam).

@@ -162,7 +162,8 @@ __device__ __forceinline__ void sl_fwd_body(const ss2d_scan_fwd_params &p, const
     auto prepare = [&](const unsigned char *sbuf, int kb, int blk, float (&uv)[OWN], float &dl_sum) {
         float dv[OWN], dl[OWN], du[OWN];
         lds_k<in_t, OWN>(reinterpret_cast<const in_t *>(sbuf + SM::d_off) + own_off + kb * BK, dv);
-        lds_own<in_t, OWN>(reinterpret_cast<const in_t *>(sbuf + SM::u_off) + own_row, OWN * ng + kb * BK, rev, uv);
+        if constexpr (CROSS) lds_own<in_t, OWN>(reinterpret_cast<const in_t *>(sbuf + SM::u_off) + own_row, OWN * ng + kb * BK, rev, uv);
+        else lds_k<in_t, OWN>(reinterpret_cast<const in_t *>(sbuf + SM::u_off) + own_off + kb * BK, uv);
         const int valid = L - (blk * BK + OWN * ng);
         dl_sum = 0.f;
 #pragma unroll

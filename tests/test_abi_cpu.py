@@ -92,3 +92,24 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
     with pytest.raises(RuntimeError, match="no CPU or PyTorch fallback"):
         _lib.lib()
+
+
+def test_hot_kernels_keep_three_ctas_per_sm():
+    """ptxas register allocation of the state-lanes kernels is fragile (an innocuous refactor of a helper took the fp32
+    forward from 136 to 177 registers = 2 instead of 3 CTAs per SM, +45 % run time): guard the budget at build time.
+    128 threads x 168 registers x 3 CTAs fits the 64 K register file."""
+    import glob
+    import os
+    import re
+    logs = glob.glob(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "focalnet_b200", "lib", "obj", "ss2d_scan_sl_*.o.log"))
+    if not logs:
+        pytest.skip("no ptxas logs (library built elsewhere)")
+    seen = 0
+    for path in logs:
+        txt = open(path).read()
+        for m in re.finditer(r"Compiling entry function '(\S+)'.*?Used (\d+) registers", txt, re.S):
+            name, regs = m.group(1), int(m.group(2))
+            if "sl_fwd_kernelIffLi2ELi4ELi64ELb1" in name or "sl_bwd_kernelIffLi2ELi4ELb1" in name or "sl_fwd_cross_kernel" in name:
+                seen += 1
+                assert regs <= 168, (name, regs)
+    assert seen >= 4
