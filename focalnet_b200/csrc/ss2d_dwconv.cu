@@ -2,228 +2,214 @@
 //
 // Replaces three separate passes of SS2D.forwardv2 (reference: ITS/models/vmamba_layers.py:591-594 with the conv
 // of :460-469): `x.permute(0,3,1,2).contiguous()` (ATen copy), `self.conv2d(x)` (cuDNN depthwise) and
-// `self.act(x)` (SiLU) — one kernel reads the in_proj output's x-half in its native (B,H,W,2*d_inner) layout and
-// writes (B,d_inner,H,W).  HBM-bound: algorithmic bytes = 4*B*H*W*C read + 4*B*C*H*W written (the 3x3 halo
-// re-reads hit L2).  Lanes walk channels on the read side and pixels on the write side; the 32x32
-// (channel, pixel) tile is turned through shared memory so both sides are 128-byte coalesced.
+// `self.act(x)` (SiLU) — one kernel reads the in_proj output's x-half in its native (B,H,W,cstride) layout and
+// writes (B,d_inner,H,W).  HBM-bound: algorithmic bytes = 4*B*H*W*C read + 4*B*C*H*W written.
 //
-// Backward: pass 1 recomputes s = conv+bias and writes dpre = dout * silu'(s) channels-last (scratch);
-// pass 2 produces dxin (correlation with the flipped taps) and reduces dweight / dbias per block before
-// one atomicAdd per (channel, tap).
+// Organisation (round 2; the round-1 kernels staged 32x32 tiles through shared memory and spent their time in 9 LDS per
+// output): **lanes = 32 consecutive channels, a thread owns a strip of 4 rows x 8 columns of ONE channel**.  Every
+// channels-last access (input pixels, dpre, dxin) is then one 128-byte line per warp instruction, the 6 x 10 input
+// window of a strip is loaded straight into registers (60 independent loads in flight per thread, halos hit L1/L2), the
+// 3x3 window slides in registers (no shared memory, no barrier), and the channels-first side moves 32 contiguous bytes
+// (one full sector) per lane and row.
+//
+// Backward: pass 1 recomputes s = conv + bias and writes dpre = dout * silu'(s) channels-last (scratch);
+// pass 2 produces dxin (correlation with the flipped taps) and accumulates dweight / dbias in registers while a warp
+// walks down its column of strips — one atomicAdd per (channel, tap) per warp.
 #include "ss2d_common.cuh"
 #include "../../include/ss2d_b200.h"
 
 namespace ss2d {
 
-constexpr int kCw = 32;   // channels per block (lanes on the channels-last side)
-constexpr int kPw = 32;   // pixels (along W) per block
-constexpr int kTy = 8;
+constexpr int kDwR = 4;      // rows per strip
+constexpr int kDwC = 8;      // columns per strip (one 32-byte sector of a channels-first row)
+constexpr int kDwWarps = 8;  // warps per CTA: 8 strips that are neighbours along W (their halos share L1 lines)
 
 struct DwGeom {
-    int B, C, H, W, tiles_w, tiles_c;
+    int B, C, H, W, strips_w, strips_h, cgroups;
     int64_t cstride;
+    bool vec;      // channels-first rows can be moved as float4 (W % 4 == 0, 16-byte aligned base)
+    int hb_per_warp;  // grad kernel: row-blocks one warp walks (register accumulation of dweight / dbias)
 };
 
-__device__ __forceinline__ void dw_decode(const DwGeom &g, int &b, int &h, int &w0, int &c0) {
-    int id = blockIdx.x;
-    c0 = (id % g.tiles_c) * kCw; id /= g.tiles_c;
-    w0 = (id % g.tiles_w) * kPw; id /= g.tiles_w;
-    h = id % g.H; b = id / g.H;
+// strip -> (b, hb, cg, ws): strips that are neighbours along W are neighbours in the index
+__device__ __forceinline__ bool dw_strip(const DwGeom &g, int64_t sid, int &b, int &hb, int &cg, int &ws) {
+    ws = (int)(sid % g.strips_w); sid /= g.strips_w;
+    cg = (int)(sid % g.cgroups); sid /= g.cgroups;
+    hb = (int)(sid % g.strips_h); sid /= g.strips_h;
+    b = (int)sid;
+    return b < g.B;
 }
 
-// Stage rows h-1..h+1, pixels w0-1..w0+kPw, channels c0..c0+31 of a channels-last tensor (zero padded).
-__device__ __forceinline__ void dw_stage(float (*tile)[kPw + 2][kCw], const float *__restrict__ src, int64_t cstride,
-                                         const DwGeom &g, int b, int h, int w0, int c0) {
-    const int tx = threadIdx.x, ty = threadIdx.y;
-    const int c = c0 + tx;
-    constexpr int kIt = (kPw + 2 + kTy - 1) / kTy;
-    float v[3][kIt];
+// the (kDwR+2) x (kDwC+2) window of a channels-last tensor around strip (hb, ws) for channel c (zero outside the image)
+__device__ __forceinline__ void dw_window(float (&v)[kDwR + 2][kDwC + 2], const float *__restrict__ src, int64_t cstride,
+                                          const DwGeom &g, int b, int h0, int w0, int c, bool active) {
 #pragma unroll
-    for (int r = 0; r < 3; ++r) {
-        const int hh = h - 1 + r;
+    for (int r = 0; r < kDwR + 2; ++r) {
+        const int hh = h0 - 1 + r;
+        const bool rok = active && hh >= 0 && hh < g.H;
+        const float *row = src + ((int64_t)b * g.H + (rok ? hh : 0)) * g.W * cstride + c;
 #pragma unroll
-        for (int k = 0; k < kIt; ++k) {
-            const int wi = ty + k * kTy, ww = w0 - 1 + wi;
-            v[r][k] = 0.f;
-            if (wi < kPw + 2 && hh >= 0 && hh < g.H && ww >= 0 && ww < g.W && c < g.C)
-                v[r][k] = __ldg(src + (((int64_t)b * g.H + hh) * g.W + ww) * cstride + c);
+        for (int j = 0; j < kDwC + 2; ++j) {
+            const int ww = w0 - 1 + j;
+            v[r][j] = (rok && ww >= 0 && ww < g.W) ? __ldg(row + (int64_t)ww * cstride) : 0.f;
         }
     }
-#pragma unroll
-    for (int r = 0; r < 3; ++r)
-#pragma unroll
-        for (int k = 0; k < kIt; ++k)
-            if (ty + k * kTy < kPw + 2) tile[r][ty + k * kTy][tx] = v[r][k];
 }
 
-// Forward: one block = 32 channels x 32 pixels x kTh rows.  The kTh+2 input rows are staged once (row re-read
-// factor (kTh+2)/kTh instead of 3), every thread produces 4*kTh outputs, and the (channel, pixel) tiles are turned
-// through shared memory so that the channels-first stores are 128-byte coalesced.
-constexpr int kTh = 4;
-__global__ void __launch_bounds__(kCw *kTy) dwconv_silu_fwd_kernel(const float *__restrict__ xin, const float *__restrict__ weight,
-                                                                  const float *__restrict__ bias, float *__restrict__ out,
-                                                                  const DwGeom g) {
-    __shared__ float tin[kTh + 2][kPw + 2][kCw];
-    __shared__ float tout[kTh][kCw][kPw + 1];
-    int id = blockIdx.x;
-    const int c0 = (id % g.tiles_c) * kCw; id /= g.tiles_c;
-    const int w0 = (id % g.tiles_w) * kPw; id /= g.tiles_w;
-    const int tiles_h = (g.H + kTh - 1) / kTh;
-    const int h0 = (id % tiles_h) * kTh, b = id / tiles_h;
-    const int tx = threadIdx.x, ty = threadIdx.y;
-    const int c = c0 + tx;
+// kDwC consecutive values of a channels-first row <-> registers
+__device__ __forceinline__ void dw_row_load(float (&o)[kDwC], const float *__restrict__ p, int nvalid, bool vec) {
+    if (vec && nvalid >= kDwC) {
+        const float4 a = __ldg(reinterpret_cast<const float4 *>(p)), b = __ldg(reinterpret_cast<const float4 *>(p) + 1);
+        o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w;
+    } else {
+#pragma unroll
+        for (int j = 0; j < kDwC; ++j) o[j] = j < nvalid ? __ldg(p + j) : 0.f;
+    }
+}
+__device__ __forceinline__ void dw_row_store(float *__restrict__ p, const float (&o)[kDwC], int nvalid, bool vec) {
+    if (vec && nvalid >= kDwC) {
+        reinterpret_cast<float4 *>(p)[0] = make_float4(o[0], o[1], o[2], o[3]);
+        reinterpret_cast<float4 *>(p)[1] = make_float4(o[4], o[5], o[6], o[7]);
+    } else {
+#pragma unroll
+        for (int j = 0; j < kDwC; ++j)
+            if (j < nvalid) p[j] = o[j];
+    }
+}
+
+__global__ void __launch_bounds__(kDwWarps *kWarp) dwconv_silu_fwd_kernel(const float *__restrict__ xin, const float *__restrict__ weight,
+                                                                         const float *__restrict__ bias, float *__restrict__ out,
+                                                                         const DwGeom g) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int b, hb, cg, ws;
+    if (!dw_strip(g, (int64_t)blockIdx.x * kDwWarps + warp, b, hb, cg, ws)) return;
+    const int c = cg * kWarp + lane, h0 = hb * kDwR, w0 = ws * kDwC;
+    const bool active = c < g.C;
     float wgt[9];
 #pragma unroll
-    for (int q = 0; q < 9; ++q) wgt[q] = c < g.C ? weight[c * 9 + q] : 0.f;
-    const float bv = (bias && c < g.C) ? bias[c] : 0.f;
-    {   // all (kTh+2) x 5 loads of a thread are issued before the first use (memory-level parallelism)
-        constexpr int kIt = (kPw + 2 + kTy - 1) / kTy;
-        float v[kTh + 2][kIt];
+    for (int q = 0; q < 9; ++q) wgt[q] = active ? __ldg(weight + c * 9 + q) : 0.f;
+    const float bv = (bias && active) ? __ldg(bias + c) : 0.f;
+    float v[kDwR + 2][kDwC + 2];
+    dw_window(v, xin, g.cstride, g, b, h0, w0, c, active);
+    if (!active) return;
 #pragma unroll
-        for (int r = 0; r < kTh + 2; ++r) {
-            const int hh = h0 - 1 + r;
+    for (int r = 0; r < kDwR; ++r) {
+        if (h0 + r >= g.H) break;
+        float o[kDwC];
 #pragma unroll
-            for (int k = 0; k < kIt; ++k) {
-                const int wi = ty + k * kTy, ww = w0 - 1 + wi;
-                v[r][k] = 0.f;
-                if (wi < kPw + 2 && hh >= 0 && hh < g.H && ww >= 0 && ww < g.W && c < g.C)
-                    v[r][k] = __ldg(xin + (((int64_t)b * g.H + hh) * g.W + ww) * g.cstride + c);
-            }
-        }
-#pragma unroll
-        for (int r = 0; r < kTh + 2; ++r)
-#pragma unroll
-            for (int k = 0; k < kIt; ++k)
-                if (ty + k * kTy < kPw + 2) tin[r][ty + k * kTy][tx] = v[r][k];
-    }
-    __syncthreads();
-#pragma unroll
-    for (int hr = 0; hr < kTh; ++hr) {
-#pragma unroll
-        for (int k = 0; k < kPw / kTy; ++k) {
-            const int wi = ty + k * kTy;
+        for (int j = 0; j < kDwC; ++j) {
             float s = bv;
 #pragma unroll
-            for (int r = 0; r < 3; ++r)
+            for (int a = 0; a < 3; ++a)
 #pragma unroll
-                for (int j = 0; j < 3; ++j) s = fmaf(wgt[r * 3 + j], tin[hr + r][wi + j][tx], s);
-            tout[hr][tx][wi] = s * sigmoidf_fast(s);
+                for (int e = 0; e < 3; ++e) s = fmaf(wgt[a * 3 + e], v[r + a][j + e], s);
+            o[j] = s * sigmoidf_fast(s);
         }
-    }
-    __syncthreads();
-#pragma unroll
-    for (int hr = 0; hr < kTh; ++hr) {
-        const int h = h0 + hr;
-#pragma unroll
-        for (int k = 0; k < kCw / kTy; ++k) {  // lanes now walk pixels: contiguous in (B,C,H,W)
-            const int cc = ty + k * kTy, w = w0 + tx;
-            if (h < g.H && c0 + cc < g.C && w < g.W) out[(((int64_t)b * g.C + c0 + cc) * g.H + h) * g.W + w] = tout[hr][cc][tx];
-        }
+        dw_row_store(out + (((int64_t)b * g.C + c) * g.H + h0 + r) * g.W + w0, o, g.W - w0, g.vec);
     }
 }
 
 // pass 1 of the backward: dpre (channels-last, dense C) = dout * silu'(conv + bias)
-__global__ void __launch_bounds__(kCw *kTy) dwconv_silu_dpre_kernel(const float *__restrict__ xin, const float *__restrict__ weight,
-                                                                   const float *__restrict__ bias, const float *__restrict__ dout,
-                                                                   float *__restrict__ dpre, const DwGeom g) {
-    __shared__ float tin[3][kPw + 2][kCw];
-    __shared__ float tg[kCw][kPw + 1];
-    int b, h, w0, c0;
-    dw_decode(g, b, h, w0, c0);
-    const int tx = threadIdx.x, ty = threadIdx.y;
-    const int c = c0 + tx;
+__global__ void __launch_bounds__(kDwWarps *kWarp) dwconv_silu_dpre_kernel(const float *__restrict__ xin, const float *__restrict__ weight,
+                                                                          const float *__restrict__ bias, const float *__restrict__ dout,
+                                                                          float *__restrict__ dpre, const DwGeom g) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int b, hb, cg, ws;
+    if (!dw_strip(g, (int64_t)blockIdx.x * kDwWarps + warp, b, hb, cg, ws)) return;
+    const int c = cg * kWarp + lane, h0 = hb * kDwR, w0 = ws * kDwC;
+    const bool active = c < g.C;
     float wgt[9];
 #pragma unroll
-    for (int q = 0; q < 9; ++q) wgt[q] = c < g.C ? weight[c * 9 + q] : 0.f;
-    const float bv = (bias && c < g.C) ? bias[c] : 0.f;
-    dw_stage(tin, xin, g.cstride, g, b, h, w0, c0);
-    for (int cc = ty; cc < kCw; cc += kTy) {
-        const int w = w0 + tx;
-        tg[cc][tx] = (c0 + cc < g.C && w < g.W) ? __ldg(dout + (((int64_t)b * g.C + c0 + cc) * g.H + h) * g.W + w) : 0.f;
-    }
-    __syncthreads();
-    for (int wi = ty; wi < kPw; wi += kTy) {
-        float s = bv;
+    for (int q = 0; q < 9; ++q) wgt[q] = active ? __ldg(weight + c * 9 + q) : 0.f;
+    const float bv = (bias && active) ? __ldg(bias + c) : 0.f;
+    float v[kDwR + 2][kDwC + 2];
+    dw_window(v, xin, g.cstride, g, b, h0, w0, c, active);
+    if (!active) return;
 #pragma unroll
-        for (int r = 0; r < 3; ++r)
+    for (int r = 0; r < kDwR; ++r) {
+        if (h0 + r >= g.H) break;
+        float go[kDwC];
+        dw_row_load(go, dout + (((int64_t)b * g.C + c) * g.H + h0 + r) * g.W + w0, g.W - w0, g.vec);
+        float *drow = dpre + (((int64_t)b * g.H + h0 + r) * g.W + w0) * g.C + c;
 #pragma unroll
-            for (int j = 0; j < 3; ++j) s = fmaf(wgt[r * 3 + j], tin[r][wi + j][tx], s);
-        const float sg = sigmoidf_fast(s);
-        const int w = w0 + wi;
-        if (c < g.C && w < g.W) dpre[(((int64_t)b * g.H + h) * g.W + w) * g.C + c] = tg[tx][wi] * sg * (1.f + s * (1.f - sg));
+        for (int j = 0; j < kDwC; ++j) {
+            float s = bv;
+#pragma unroll
+            for (int a = 0; a < 3; ++a)
+#pragma unroll
+                for (int e = 0; e < 3; ++e) s = fmaf(wgt[a * 3 + e], v[r + a][j + e], s);
+            const float sg = sigmoidf_fast(s);
+            if (w0 + j < g.W) drow[(int64_t)j * g.C] = go[j] * sg * (1.f + s * (1.f - sg));
+        }
     }
 }
 
 // pass 2: dxin = corr(dpre, flipped taps); dweight[c][tap] += sum dpre * xin(shifted); dbias[c] += sum dpre.
-// One block walks kGradRows rows x all W tiles of its 32-channel slab, so the dweight / dbias partial sums stay in
-// registers across ~32 tiles and only one atomicAdd per (channel, tap) per block reaches L2 (the first version
-// issued one per tile: 31 M atomics onto 1920 addresses at the training shape).
-constexpr int kGradRows = 8;
-__global__ void __launch_bounds__(kCw *kTy) dwconv_silu_grad_kernel(const float *__restrict__ xin, const float *__restrict__ weight,
-                                                                   const float *__restrict__ dpre, float *__restrict__ dxin,
-                                                                   int64_t dx_cstride, float *__restrict__ dweight,
-                                                                   float *__restrict__ dbias, const DwGeom g) {
-    __shared__ float tin[3][kPw + 2][kCw];
-    __shared__ float tdp[3][kPw + 2][kCw];
-    __shared__ float red[kTy][10][kCw];
-    int id = blockIdx.x;
-    const int c0 = (id % g.tiles_c) * kCw; id /= g.tiles_c;
-    const int hblocks = (g.H + kGradRows - 1) / kGradRows;
-    const int hb = id % hblocks, b = id / hblocks;
-    const int tx = threadIdx.x, ty = threadIdx.y;
-    const int c = c0 + tx;
-    float wgt[9];
+// A warp walks hb_per_warp row-blocks of its column of strips, so the dweight / dbias partial sums stay in registers and
+// one atomicAdd per (channel, tap) per warp reaches L2.
+__global__ void __launch_bounds__(kDwWarps *kWarp) dwconv_silu_grad_kernel(const float *__restrict__ xin, const float *__restrict__ weight,
+                                                                          const float *__restrict__ dpre, float *__restrict__ dxin,
+                                                                          int64_t dx_cstride, float *__restrict__ dweight,
+                                                                          float *__restrict__ dbias, const DwGeom g) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // walk index -> (b, hchunk, cg, ws)
+    int64_t sid = (int64_t)blockIdx.x * kDwWarps + warp;
+    const int hchunks = (g.strips_h + g.hb_per_warp - 1) / g.hb_per_warp;
+    const int ws = (int)(sid % g.strips_w); sid /= g.strips_w;
+    const int cg = (int)(sid % g.cgroups); sid /= g.cgroups;
+    const int hc = (int)(sid % hchunks); sid /= hchunks;
+    const int b = (int)sid;
+    if (b >= g.B) return;
+    const int c = cg * kWarp + lane, w0 = ws * kDwC;
+    const bool active = c < g.C;
+    float wgt[9], acc[10];
 #pragma unroll
-    for (int q = 0; q < 9; ++q) wgt[q] = c < g.C ? weight[c * 9 + q] : 0.f;
-    float acc[10];
+    for (int q = 0; q < 9; ++q) wgt[q] = active ? __ldg(weight + c * 9 + q) : 0.f;
 #pragma unroll
     for (int q = 0; q < 10; ++q) acc[q] = 0.f;
-    const int h_end = min(g.H, (hb + 1) * kGradRows);
-    for (int h = hb * kGradRows; h < h_end; ++h) {
-        for (int wt = 0; wt < g.tiles_w; ++wt) {
-            const int w0 = wt * kPw;
-            __syncthreads();  // previous tile fully consumed
-            dw_stage(tin, xin, g.cstride, g, b, h, w0, c0);
-            dw_stage(tdp, dpre, g.C, g, b, h, w0, c0);
-            __syncthreads();
+    const int hb_end = min(g.strips_h, (hc + 1) * g.hb_per_warp);
+    for (int hb = hc * g.hb_per_warp; hb < hb_end; ++hb) {
+        const int h0 = hb * kDwR;
+        float dp[kDwR + 2][kDwC + 2], xv[kDwR + 2][kDwC + 2];
+        dw_window(dp, dpre, g.C, g, b, h0, w0, c, active);
+        dw_window(xv, xin, g.cstride, g, b, h0, w0, c, active);
+        if (!active) continue;
 #pragma unroll
-            for (int k = 0; k < kPw / kTy; ++k) {
-                const int wi = ty + k * kTy, w = w0 + wi;
-                // input pixel (h, w) was read by output pixel (h+1-r, w+1-j) through tap (r, j)
+        for (int r = 0; r < kDwR; ++r) {
+            if (h0 + r >= g.H) break;
+            float *xrow = dxin + (((int64_t)b * g.H + h0 + r) * g.W + w0) * dx_cstride + c;
+#pragma unroll
+            for (int j = 0; j < kDwC; ++j) {
+                // input pixel (h, w) was read by output pixel (h+1-a, w+1-e) through tap (a, e)
                 float s = 0.f;
 #pragma unroll
-                for (int r = 0; r < 3; ++r)
+                for (int a = 0; a < 3; ++a)
 #pragma unroll
-                    for (int j = 0; j < 3; ++j) s = fmaf(wgt[r * 3 + j], tdp[2 - r][wi + 2 - j][tx], s);
-                if (c < g.C && w < g.W) dxin[(((int64_t)b * g.H + h) * g.W + w) * dx_cstride + c] = s;
-                const float gp = tdp[1][wi + 1][tx];  // dpre at output pixel (h, w); zero outside the image
+                    for (int e = 0; e < 3; ++e) s = fmaf(wgt[a * 3 + e], dp[r + 2 - a][j + 2 - e], s);
+                if (w0 + j < g.W) xrow[(int64_t)j * dx_cstride] = s;
+                const float gp = dp[r + 1][j + 1];  // dpre at output pixel (h, w): zero outside the image
 #pragma unroll
-                for (int r = 0; r < 3; ++r)
+                for (int a = 0; a < 3; ++a)
 #pragma unroll
-                    for (int j = 0; j < 3; ++j) acc[r * 3 + j] = fmaf(gp, tin[r][wi + j][tx], acc[r * 3 + j]);
+                    for (int e = 0; e < 3; ++e) acc[a * 3 + e] = fmaf(gp, xv[r + a][j + e], acc[a * 3 + e]);
                 acc[9] += gp;
             }
         }
     }
+    if (active) {
 #pragma unroll
-    for (int q = 0; q < 10; ++q) red[ty][q][tx] = acc[q];
-    __syncthreads();
-    for (int q = ty; q < 10; q += kTy) {
-        float s = 0.f;
-#pragma unroll
-        for (int t = 0; t < kTy; ++t) s += red[t][q][tx];
-        if (c < g.C) {
-            if (q < 9) atomicAdd(dweight + c * 9 + q, s);
-            else if (dbias) atomicAdd(dbias + c, s);
-        }
+        for (int q = 0; q < 9; ++q) atomicAdd(dweight + c * 9 + q, acc[q]);
+        if (dbias) atomicAdd(dbias + c, acc[9]);
     }
 }
 
-static int dw_geom(DwGeom &g, int64_t cstride, int64_t B, int64_t C, int64_t H, int64_t W) {
+static int dw_geom(DwGeom &g, int64_t cstride, int64_t B, int64_t C, int64_t H, int64_t W, const void *cf_ptr) {
     if (B <= 0 || C <= 0 || H <= 0 || W <= 0 || cstride < C) return SS2D_EINVAL;
     g.B = (int)B; g.C = (int)C; g.H = (int)H; g.W = (int)W; g.cstride = cstride;
-    g.tiles_w = (int)((W + kPw - 1) / kPw); g.tiles_c = (int)((C + kCw - 1) / kCw);
-    if ((int64_t)g.tiles_w * g.tiles_c * H * B > 0x7fffffffLL) return SS2D_EINVAL;
+    g.strips_w = (int)((W + kDwC - 1) / kDwC); g.strips_h = (int)((H + kDwR - 1) / kDwR); g.cgroups = (int)((C + kWarp - 1) / kWarp);
+    g.vec = W % 4 == 0 && (reinterpret_cast<uintptr_t>(cf_ptr) & 15) == 0;
+    g.hb_per_warp = 1;
+    if ((int64_t)g.strips_w * g.strips_h * g.cgroups * B / kDwWarps + 1 > 0x7fffffffLL) return SS2D_EINVAL;
     return 0;
 }
 
@@ -234,9 +220,10 @@ extern "C" int ss2d_dwconv_silu_fwd(const float *xin, int64_t cstride, const flo
     using namespace ss2d;
     if (!xin || !weight || !out) return SS2D_EINVAL;
     DwGeom g;
-    if (int rc = dw_geom(g, cstride, batch, C, H, W)) return rc;
-    const unsigned grid = (unsigned)((int64_t)g.tiles_w * g.tiles_c * ((H + kTh - 1) / kTh) * batch);
-    dwconv_silu_fwd_kernel<<<grid, dim3(kCw, kTy), 0, reinterpret_cast<cudaStream_t>(stream)>>>(xin, weight, bias, out, g);
+    if (int rc = dw_geom(g, cstride, batch, C, H, W, out)) return rc;
+    const int64_t strips = (int64_t)g.strips_w * g.strips_h * g.cgroups * batch;
+    dwconv_silu_fwd_kernel<<<(unsigned)((strips + kDwWarps - 1) / kDwWarps), kDwWarps * kWarp, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        xin, weight, bias, out, g);
     return (int)cudaGetLastError();
 }
 
@@ -246,11 +233,18 @@ extern "C" int ss2d_dwconv_silu_bwd(const float *xin, int64_t cstride, const flo
     using namespace ss2d;
     if (!xin || !weight || !dout || !dpre_scratch || !dxin || !dweight || dx_cstride < C) return SS2D_EINVAL;
     DwGeom g;
-    if (int rc = dw_geom(g, cstride, batch, C, H, W)) return rc;
-    const unsigned grid = (unsigned)((int64_t)g.tiles_w * g.tiles_c * H * batch);
+    if (int rc = dw_geom(g, cstride, batch, C, H, W, dout)) return rc;
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-    dwconv_silu_dpre_kernel<<<grid, dim3(kCw, kTy), 0, s>>>(xin, weight, bias, dout, dpre_scratch, g);
-    const unsigned grid2 = (unsigned)((int64_t)g.tiles_c * ((H + kGradRows - 1) / kGradRows) * batch);
-    dwconv_silu_grad_kernel<<<grid2, dim3(kCw, kTy), 0, s>>>(xin, weight, dpre_scratch, dxin, dx_cstride, dweight, dbias, g);
+    const int64_t strips = (int64_t)g.strips_w * g.strips_h * g.cgroups * batch;
+    dwconv_silu_dpre_kernel<<<(unsigned)((strips + kDwWarps - 1) / kDwWarps), kDwWarps * kWarp, 0, s>>>(xin, weight, bias, dout, dpre_scratch, g);
+    // row-blocks per warp in pass 2: as many as keeps >= ~8 warps per SM sub-partition in flight (fewer atomics per tap)
+    const int64_t want_warps = 148 * 4 * 8;
+    int64_t hbpw = strips / want_warps;
+    hbpw = hbpw < 1 ? 1 : (hbpw > g.strips_h ? g.strips_h : hbpw);
+    g.hb_per_warp = (int)hbpw;
+    const int64_t hchunks = (g.strips_h + hbpw - 1) / hbpw;
+    const int64_t walks = (int64_t)g.strips_w * g.cgroups * hchunks * batch;
+    dwconv_silu_grad_kernel<<<(unsigned)((walks + kDwWarps - 1) / kDwWarps), kDwWarps * kWarp, 0, s>>>(xin, weight, dpre_scratch, dxin, dx_cstride,
+                                                                                                       dweight, dbias, g);
     return (int)cudaGetLastError();
 }

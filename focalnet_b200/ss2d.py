@@ -408,10 +408,15 @@ def ss2d_forward(m: torch.nn.Module, x: torch.Tensor) -> torch.Tensor:
     with the fused core."""
     if not block_supported(m) or torch.is_autocast_enabled() or x.dtype != torch.float32:
         return m.forwardv2(x)
-    xz = m.in_proj(x)                                        # (B, H, W, 2*d_inner)
-    B, H, W, _ = xz.shape
     D = m.conv2d.out_channels
-    xc = dwconv_silu(xz.contiguous(), m.conv2d.weight, m.conv2d.bias, D)
+    # in_proj as two GEMMs over the two halves of its weight (the same dot products as ONE F.linear + chunk(2), :585-587):
+    # the x half and the z half come out as separate dense tensors, so the backward never builds the (B,H,W,2*d_inner)
+    # gradient by zero-filling it twice and adding the two halves' contributions (3.5 GB of traffic per call at B=32, 128x128)
+    bias = m.in_proj.bias
+    xh = F.linear(x, m.in_proj.weight[:D], None if bias is None else bias[:D])     # (B, H, W, d_inner)
+    zh = F.linear(x, m.in_proj.weight[D:], None if bias is None else bias[D:])
+    B, H, W, _ = xh.shape
+    xc = dwconv_silu(xh, m.conv2d.weight, m.conv2d.bias, D)
     N = m.A_logs.shape[1]
     K, _, R = m.dt_projs_weight.shape
     L = H * W
@@ -420,7 +425,7 @@ def ss2d_forward(m: torch.nn.Module, x: torch.Tensor) -> torch.Tensor:
     dts_lr, Bs, Cs = torch.split(x_dbl, [R, N, N], dim=2)
     dts = F.conv1d(dts_lr.reshape(B, K * R, L), m.dt_projs_weight.reshape(K * D, R, 1), groups=K)
     y = FusedCrossScanFn.apply(xc, dts, -torch.exp(m.A_logs.float()), Bs, Cs, m.Ds.float(), m.dt_projs_bias.reshape(-1).float(), True)
-    y = merge_norm_gate(y, m.out_norm.weight, m.out_norm.bias, m.out_norm.eps, z=xz[..., D:]).view(B, H, W, D)
+    y = merge_norm_gate(y, m.out_norm.weight, m.out_norm.bias, m.out_norm.eps, z=zh).view(B, H, W, D)
     return m.dropout(m.out_proj(y))
 
 
@@ -483,7 +488,7 @@ class DwConvSiLUFn(torch.autograd.Function):
         B, H, W, Cs = xz.shape
         Cn = ctx.Cn
         dout = dout.contiguous().float()
-        dxz = torch.zeros_like(xz)
+        dxz = torch.empty_like(xz) if Cs == Cn else torch.zeros_like(xz)  # dense input: every element is written
         dw = torch.zeros_like(w)
         db = torch.zeros(Cn, device=xz.device, dtype=torch.float32) if ctx.has_bias else None
         scratch = torch.empty((B, H, W, Cn), device=xz.device, dtype=torch.float32)

@@ -59,3 +59,18 @@ for (B, D, H, W, tag) in [(8, 192, 64, 64, "micro"), (32, 192, 128, 128, "train-
     def refmix():
         return torch.nn.functional.silu(conv(xz.detach()[..., :D].permute(0, 3, 1, 2).contiguous()))
     rep(f"[{tag} float32] reference pre-mix (ATen+cuDNN)", timeit(refmix), 8 * B * D * L)
+    # dense d_inner-channel input (what ss2d_forward feeds since round 2: in_proj split into x-half / z-half GEMMs)
+    xh = torch.randn(B, H, W, D).cuda().requires_grad_()
+    rep(f"[{tag} float32] dwconv fwd, dense input", timeit(lambda: dwconv_silu(xh.detach(), w.detach(), bb.detach(), D)), 8 * B * D * L)
+    def db2():
+        y2 = dwconv_silu(xh, w, bb, D); torch.autograd.grad(y2, (xh, w, bb), gg)
+    rep(f"[{tag} float32] dwconv fwd+bwd, dense input", timeit(db2, n=10), 8 * B * D * L + 4 * B * D * L * 5)
+    from focalnet_b200 import merge_norm_gate
+    ym = torch.randn(B, D, L).cuda().requires_grad_()
+    zz = torch.randn(B, H, W, D).cuda().requires_grad_()
+    lw, lb = torch.ones(D).cuda().requires_grad_(), torch.zeros(D).cuda().requires_grad_()
+    rep(f"[{tag} float32] merge+LayerNorm+gate fwd", timeit(lambda: merge_norm_gate(ym.detach(), lw.detach(), lb.detach(), 1e-5, z=zz.detach())), 12 * B * D * L)
+    go = torch.randn(B, L, D).cuda()
+    def mb():
+        o = merge_norm_gate(ym, lw, lb, 1e-5, z=zz); torch.autograd.grad(o, (ym, lw, lb, zz), go)
+    rep(f"[{tag} float32] merge+LayerNorm+gate fwd+bwd", timeit(mb, n=10), 12 * B * D * L + 20 * B * D * L)
