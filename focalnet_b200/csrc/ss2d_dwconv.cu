@@ -6,53 +6,54 @@
 // writes (B,d_inner,H,W).  HBM-bound: algorithmic bytes = 4*B*H*W*C read + 4*B*C*H*W written.
 //
 // Organisation (round 2; the round-1 kernels staged 32x32 tiles through shared memory and spent their time in 9 LDS per
-// output): **lanes = 32 consecutive channels, a thread owns a strip of 4 rows x 8 columns of ONE channel**.  Every
-// channels-last access (input pixels, dpre, dxin) is then one 128-byte line per warp instruction, the 6 x 10 input
-// window of a strip is loaded straight into registers (60 independent loads in flight per thread, halos hit L1/L2), the
-// 3x3 window slides in registers (no shared memory, no barrier), and the channels-first side moves 32 contiguous bytes
-// (one full sector) per lane and row.
+// output): **lanes = 32 consecutive channels; a warp walks DOWN a strip of 8 columns** with the 3-row x 10-column input
+// window of its channel sliding through registers (4 row buffers: the row two below the one being computed is in flight
+// while the current row is evaluated).  Every channels-last access (input pixels, dpre, dxin) is one 128-byte line per
+// warp instruction, each input value is loaded 1.25 times (column halo only), there is no shared memory and no barrier,
+// and the channels-first side moves 32 contiguous bytes (one full sector) per lane and row.  Strips whose 10 columns lie
+// inside the image take a path without column predicates.
 //
 // Backward: pass 1 recomputes s = conv + bias and writes dpre = dout * silu'(s) channels-last (scratch);
-// pass 2 produces dxin (correlation with the flipped taps) and accumulates dweight / dbias in registers while a warp
-// walks down its column of strips — one atomicAdd per (channel, tap) per warp.
+// pass 2 produces dxin (correlation with the flipped taps) and accumulates dweight / dbias in registers while the warp
+// walks its chunk of rows — one atomicAdd per (channel, tap) per warp.
 #include "ss2d_common.cuh"
 #include "../../include/ss2d_b200.h"
 
 namespace ss2d {
 
-constexpr int kDwR = 4;      // rows per strip
 constexpr int kDwC = 8;      // columns per strip (one 32-byte sector of a channels-first row)
-constexpr int kDwWarps = 8;  // warps per CTA: 8 strips that are neighbours along W (their halos share L1 lines)
+constexpr int kDwWin = kDwC + 2;
+constexpr int kDwWarps = 4;  // warps per CTA: strips that are neighbours along W (their column halos share L1 lines)
 
 struct DwGeom {
-    int B, C, H, W, strips_w, strips_h, cgroups;
+    int B, C, H, W, strips_w, cgroups, rows_per_walk, hchunks;
     int64_t cstride;
-    bool vec;      // channels-first rows can be moved as float4 (W % 4 == 0, 16-byte aligned base)
-    int hb_per_warp;  // grad kernel: row-blocks one warp walks (register accumulation of dweight / dbias)
+    bool vec;  // channels-first rows can be moved as float4 (W % 4 == 0, 16-byte aligned base)
 };
 
-// strip -> (b, hb, cg, ws): strips that are neighbours along W are neighbours in the index
-__device__ __forceinline__ bool dw_strip(const DwGeom &g, int64_t sid, int &b, int &hb, int &cg, int &ws) {
-    ws = (int)(sid % g.strips_w); sid /= g.strips_w;
-    cg = (int)(sid % g.cgroups); sid /= g.cgroups;
-    hb = (int)(sid % g.strips_h); sid /= g.strips_h;
-    b = (int)sid;
+// walk -> (b, hc, cg, ws): walks that are neighbours along W are neighbours in the index
+__device__ __forceinline__ bool dw_walk(const DwGeom &g, int64_t id, int &b, int &hc, int &cg, int &ws) {
+    ws = (int)(id % g.strips_w); id /= g.strips_w;
+    cg = (int)(id % g.cgroups); id /= g.cgroups;
+    hc = (int)(id % g.hchunks); id /= g.hchunks;
+    b = (int)id;
     return b < g.B;
 }
 
-// the (kDwR+2) x (kDwC+2) window of a channels-last tensor around strip (hb, ws) for channel c (zero outside the image)
-__device__ __forceinline__ void dw_window(float (&v)[kDwR + 2][kDwC + 2], const float *__restrict__ src, int64_t cstride,
-                                          const DwGeom &g, int b, int h0, int w0, int c, bool active) {
+// one row (10 columns around the strip) of a channels-last tensor for this lane's channel; zero outside the image.
+// `img` points at pixel (b, 0, 0), channel c.
+template <bool INTERIOR>
+__device__ __forceinline__ void dw_load_row(float (&r)[kDwWin], const float *__restrict__ img, int64_t cstride, int hh, int H, int W, int w0) {
+    if (hh < 0 || hh >= H) {  // warp-uniform
 #pragma unroll
-    for (int r = 0; r < kDwR + 2; ++r) {
-        const int hh = h0 - 1 + r;
-        const bool rok = active && hh >= 0 && hh < g.H;
-        const float *row = src + ((int64_t)b * g.H + (rok ? hh : 0)) * g.W * cstride + c;
+        for (int j = 0; j < kDwWin; ++j) r[j] = 0.f;
+        return;
+    }
+    const float *p = img + ((int64_t)hh * W + (w0 - 1)) * cstride;
 #pragma unroll
-        for (int j = 0; j < kDwC + 2; ++j) {
-            const int ww = w0 - 1 + j;
-            v[r][j] = (rok && ww >= 0 && ww < g.W) ? __ldg(row + (int64_t)ww * cstride) : 0.f;
-        }
+    for (int j = 0; j < kDwWin; ++j) {
+        r[j] = (INTERIOR || (w0 - 1 + j >= 0 && w0 - 1 + j < W)) ? __ldg(p) : 0.f;
+        p += cstride;
     }
 }
 
@@ -77,140 +78,170 @@ __device__ __forceinline__ void dw_row_store(float *__restrict__ p, const float 
     }
 }
 
-__global__ void __launch_bounds__(kDwWarps *kWarp) dwconv_silu_fwd_kernel(const float *__restrict__ xin, const float *__restrict__ weight,
-                                                                         const float *__restrict__ bias, float *__restrict__ out,
-                                                                         const DwGeom g) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    int b, hb, cg, ws;
-    if (!dw_strip(g, (int64_t)blockIdx.x * kDwWarps + warp, b, hb, cg, ws)) return;
-    const int c = cg * kWarp + lane, h0 = hb * kDwR, w0 = ws * kDwC;
-    const bool active = c < g.C;
-    float wgt[9];
+__device__ __forceinline__ float dw_conv_at(const float (&wgt)[9], float bv, const float (&ra)[kDwWin], const float (&rb)[kDwWin],
+                                            const float (&rc)[kDwWin], int j) {
+    float s = bv;
 #pragma unroll
-    for (int q = 0; q < 9; ++q) wgt[q] = active ? __ldg(weight + c * 9 + q) : 0.f;
-    const float bv = (bias && active) ? __ldg(bias + c) : 0.f;
-    float v[kDwR + 2][kDwC + 2];
-    dw_window(v, xin, g.cstride, g, b, h0, w0, c, active);
-    if (!active) return;
+    for (int e = 0; e < 3; ++e) {
+        s = fmaf(wgt[e], ra[j + e], s);
+        s = fmaf(wgt[3 + e], rb[j + e], s);
+        s = fmaf(wgt[6 + e], rc[j + e], s);
+    }
+    return s;
+}
+
+enum { kDwFwd = 0, kDwDpre = 1 };
+
+// forward (MODE kDwFwd: out = silu(conv + bias), channels-first) and pass 1 of the backward (MODE kDwDpre: dpre = dout *
+// silu'(conv + bias), channels-last dense C).  `cf` is the channels-first tensor of the mode (out resp. dout).
+template <int MODE, bool INTERIOR>
+__device__ __forceinline__ void dw_walk_rows(const float *__restrict__ xin, const float (&wgt)[9], float bv, float *__restrict__ out,
+                                             const float *__restrict__ dout, float *__restrict__ dpre, const DwGeom &g, int b, int c,
+                                             int h_begin, int h_end, int w0) {
+    const float *img = xin + (int64_t)b * g.H * g.W * g.cstride + c;
+    float win[4][kDwWin];
+    // h_begin is a multiple of 4 (rows_per_walk is): row h lives in buffer h & 3, all buffer indices are compile-time constants
+    dw_load_row<INTERIOR>(win[3], img, g.cstride, h_begin - 1, g.H, g.W, w0);
+    dw_load_row<INTERIOR>(win[0], img, g.cstride, h_begin, g.H, g.W, w0);
+    dw_load_row<INTERIOR>(win[1], img, g.cstride, h_begin + 1, g.H, g.W, w0);
+#pragma unroll 1
+    for (int h4 = h_begin; h4 < h_end; h4 += 4) {
 #pragma unroll
-    for (int r = 0; r < kDwR; ++r) {
-        if (h0 + r >= g.H) break;
-        float o[kDwC];
+        for (int k = 0; k < 4; ++k) {
+            const int h = h4 + k;
+            if (h >= h_end) break;
+            dw_load_row<INTERIOR>(win[(k + 2) & 3], img, g.cstride, h + 2, g.H, g.W, w0);  // in flight while row h is evaluated
+            float (&ra)[kDwWin] = win[(k + 3) & 3], (&rb)[kDwWin] = win[k], (&rc)[kDwWin] = win[(k + 1) & 3];
+            const int64_t cf_off = (((int64_t)b * g.C + c) * g.H + h) * g.W + w0;
+            if constexpr (MODE == kDwFwd) {
+                float o[kDwC];
 #pragma unroll
-        for (int j = 0; j < kDwC; ++j) {
-            float s = bv;
+                for (int j = 0; j < kDwC; ++j) {
+                    const float s = dw_conv_at(wgt, bv, ra, rb, rc, j);
+                    o[j] = s * sigmoidf_fast(s);
+                }
+                dw_row_store(out + cf_off, o, g.W - w0, g.vec);
+            } else {
+                float go[kDwC];
+                dw_row_load(go, dout + cf_off, g.W - w0, g.vec);
+                float *drow = dpre + (((int64_t)b * g.H + h) * g.W + w0) * g.C + c;
 #pragma unroll
-            for (int a = 0; a < 3; ++a)
-#pragma unroll
-                for (int e = 0; e < 3; ++e) s = fmaf(wgt[a * 3 + e], v[r + a][j + e], s);
-            o[j] = s * sigmoidf_fast(s);
+                for (int j = 0; j < kDwC; ++j) {
+                    const float s = dw_conv_at(wgt, bv, ra, rb, rc, j);
+                    const float sg = sigmoidf_fast(s);
+                    if (INTERIOR || w0 + j < g.W) drow[(int64_t)j * g.C] = go[j] * sg * (1.f + s * (1.f - sg));
+                }
+            }
         }
-        dw_row_store(out + (((int64_t)b * g.C + c) * g.H + h0 + r) * g.W + w0, o, g.W - w0, g.vec);
     }
 }
 
-// pass 1 of the backward: dpre (channels-last, dense C) = dout * silu'(conv + bias)
-__global__ void __launch_bounds__(kDwWarps *kWarp) dwconv_silu_dpre_kernel(const float *__restrict__ xin, const float *__restrict__ weight,
-                                                                          const float *__restrict__ bias, const float *__restrict__ dout,
-                                                                          float *__restrict__ dpre, const DwGeom g) {
+template <int MODE>
+__global__ void __launch_bounds__(kDwWarps *kWarp, 5) dwconv_silu_walk_kernel(const float *__restrict__ xin, const float *__restrict__ weight,
+                                                                             const float *__restrict__ bias, float *__restrict__ out,
+                                                                             const float *__restrict__ dout, float *__restrict__ dpre,
+                                                                             const DwGeom g) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    int b, hb, cg, ws;
-    if (!dw_strip(g, (int64_t)blockIdx.x * kDwWarps + warp, b, hb, cg, ws)) return;
-    const int c = cg * kWarp + lane, h0 = hb * kDwR, w0 = ws * kDwC;
-    const bool active = c < g.C;
+    int b, hc, cg, ws;
+    if (!dw_walk(g, (int64_t)blockIdx.x * kDwWarps + warp, b, hc, cg, ws)) return;
+    const int c = cg * kWarp + lane, w0 = ws * kDwC;
+    if (c >= g.C) return;
     float wgt[9];
 #pragma unroll
-    for (int q = 0; q < 9; ++q) wgt[q] = active ? __ldg(weight + c * 9 + q) : 0.f;
-    const float bv = (bias && active) ? __ldg(bias + c) : 0.f;
-    float v[kDwR + 2][kDwC + 2];
-    dw_window(v, xin, g.cstride, g, b, h0, w0, c, active);
-    if (!active) return;
-#pragma unroll
-    for (int r = 0; r < kDwR; ++r) {
-        if (h0 + r >= g.H) break;
-        float go[kDwC];
-        dw_row_load(go, dout + (((int64_t)b * g.C + c) * g.H + h0 + r) * g.W + w0, g.W - w0, g.vec);
-        float *drow = dpre + (((int64_t)b * g.H + h0 + r) * g.W + w0) * g.C + c;
-#pragma unroll
-        for (int j = 0; j < kDwC; ++j) {
-            float s = bv;
-#pragma unroll
-            for (int a = 0; a < 3; ++a)
-#pragma unroll
-                for (int e = 0; e < 3; ++e) s = fmaf(wgt[a * 3 + e], v[r + a][j + e], s);
-            const float sg = sigmoidf_fast(s);
-            if (w0 + j < g.W) drow[(int64_t)j * g.C] = go[j] * sg * (1.f + s * (1.f - sg));
-        }
-    }
+    for (int q = 0; q < 9; ++q) wgt[q] = __ldg(weight + c * 9 + q);
+    const float bv = bias ? __ldg(bias + c) : 0.f;
+    const int h_begin = hc * g.rows_per_walk, h_end = min(g.H, h_begin + g.rows_per_walk);
+    if (w0 >= 1 && w0 + kDwC + 1 <= g.W) dw_walk_rows<MODE, true>(xin, wgt, bv, out, dout, dpre, g, b, c, h_begin, h_end, w0);
+    else dw_walk_rows<MODE, false>(xin, wgt, bv, out, dout, dpre, g, b, c, h_begin, h_end, w0);
 }
 
 // pass 2: dxin = corr(dpre, flipped taps); dweight[c][tap] += sum dpre * xin(shifted); dbias[c] += sum dpre.
-// A warp walks hb_per_warp row-blocks of its column of strips, so the dweight / dbias partial sums stay in registers and
-// one atomicAdd per (channel, tap) per warp reaches L2.
-__global__ void __launch_bounds__(kDwWarps *kWarp) dwconv_silu_grad_kernel(const float *__restrict__ xin, const float *__restrict__ weight,
-                                                                          const float *__restrict__ dpre, float *__restrict__ dxin,
-                                                                          int64_t dx_cstride, float *__restrict__ dweight,
-                                                                          float *__restrict__ dbias, const DwGeom g) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    // walk index -> (b, hchunk, cg, ws)
-    int64_t sid = (int64_t)blockIdx.x * kDwWarps + warp;
-    const int hchunks = (g.strips_h + g.hb_per_warp - 1) / g.hb_per_warp;
-    const int ws = (int)(sid % g.strips_w); sid /= g.strips_w;
-    const int cg = (int)(sid % g.cgroups); sid /= g.cgroups;
-    const int hc = (int)(sid % hchunks); sid /= hchunks;
-    const int b = (int)sid;
-    if (b >= g.B) return;
-    const int c = cg * kWarp + lane, w0 = ws * kDwC;
-    const bool active = c < g.C;
-    float wgt[9], acc[10];
+template <bool INTERIOR>
+__device__ __forceinline__ void dw_grad_rows(const float *__restrict__ xin, const float *__restrict__ dpre, const float (&wgt)[9],
+                                             float *__restrict__ dxin, int64_t dx_cstride, float (&acc)[10], const DwGeom &g, int b, int c,
+                                             int h_begin, int h_end, int w0) {
+    const float *ximg = xin + (int64_t)b * g.H * g.W * g.cstride + c;
+    const float *dimg = dpre + (int64_t)b * g.H * g.W * g.C + c;
+    float xw[4][kDwWin], dw[4][kDwWin];
 #pragma unroll
-    for (int q = 0; q < 9; ++q) wgt[q] = active ? __ldg(weight + c * 9 + q) : 0.f;
+    for (int k = -1; k <= 1; ++k) {  // h_begin % 4 == 0: row h lives in buffer h & 3
+        dw_load_row<INTERIOR>(xw[k & 3], ximg, g.cstride, h_begin + k, g.H, g.W, w0);
+        dw_load_row<INTERIOR>(dw[k & 3], dimg, g.C, h_begin + k, g.H, g.W, w0);
+    }
+#pragma unroll 1
+    for (int h4 = h_begin; h4 < h_end; h4 += 4) {
 #pragma unroll
-    for (int q = 0; q < 10; ++q) acc[q] = 0.f;
-    const int hb_end = min(g.strips_h, (hc + 1) * g.hb_per_warp);
-    for (int hb = hc * g.hb_per_warp; hb < hb_end; ++hb) {
-        const int h0 = hb * kDwR;
-        float dp[kDwR + 2][kDwC + 2], xv[kDwR + 2][kDwC + 2];
-        dw_window(dp, dpre, g.C, g, b, h0, w0, c, active);
-        dw_window(xv, xin, g.cstride, g, b, h0, w0, c, active);
-        if (!active) continue;
-#pragma unroll
-        for (int r = 0; r < kDwR; ++r) {
-            if (h0 + r >= g.H) break;
-            float *xrow = dxin + (((int64_t)b * g.H + h0 + r) * g.W + w0) * dx_cstride + c;
+        for (int k = 0; k < 4; ++k) {
+            const int h = h4 + k;
+            if (h >= h_end) break;
+            dw_load_row<INTERIOR>(xw[(k + 2) & 3], ximg, g.cstride, h + 2, g.H, g.W, w0);
+            dw_load_row<INTERIOR>(dw[(k + 2) & 3], dimg, g.C, h + 2, g.H, g.W, w0);
+            float (&xa)[kDwWin] = xw[(k + 3) & 3], (&xb)[kDwWin] = xw[k], (&xc)[kDwWin] = xw[(k + 1) & 3];
+            float (&da)[kDwWin] = dw[(k + 3) & 3], (&db)[kDwWin] = dw[k], (&dc)[kDwWin] = dw[(k + 1) & 3];
+            float *xrow = dxin + (((int64_t)b * g.H + h) * g.W + w0) * dx_cstride + c;
 #pragma unroll
             for (int j = 0; j < kDwC; ++j) {
-                // input pixel (h, w) was read by output pixel (h+1-a, w+1-e) through tap (a, e)
+                // input pixel (h, w) was read by output pixel (h+1-a, w+1-e) through tap (a, e): rows h+1, h, h-1 of dpre
                 float s = 0.f;
 #pragma unroll
-                for (int a = 0; a < 3; ++a)
+                for (int e = 0; e < 3; ++e) {
+                    s = fmaf(wgt[e], dc[j + 2 - e], s);
+                    s = fmaf(wgt[3 + e], db[j + 2 - e], s);
+                    s = fmaf(wgt[6 + e], da[j + 2 - e], s);
+                }
+                if (INTERIOR || w0 + j < g.W) xrow[(int64_t)j * dx_cstride] = s;
+                const float gp = db[j + 1];  // dpre at output pixel (h, w): zero outside the image
 #pragma unroll
-                    for (int e = 0; e < 3; ++e) s = fmaf(wgt[a * 3 + e], dp[r + 2 - a][j + 2 - e], s);
-                if (w0 + j < g.W) xrow[(int64_t)j * dx_cstride] = s;
-                const float gp = dp[r + 1][j + 1];  // dpre at output pixel (h, w): zero outside the image
-#pragma unroll
-                for (int a = 0; a < 3; ++a)
-#pragma unroll
-                    for (int e = 0; e < 3; ++e) acc[a * 3 + e] = fmaf(gp, xv[r + a][j + e], acc[a * 3 + e]);
+                for (int e = 0; e < 3; ++e) {
+                    acc[e] = fmaf(gp, xa[j + e], acc[e]);
+                    acc[3 + e] = fmaf(gp, xb[j + e], acc[3 + e]);
+                    acc[6 + e] = fmaf(gp, xc[j + e], acc[6 + e]);
+                }
                 acc[9] += gp;
             }
         }
     }
-    if (active) {
-#pragma unroll
-        for (int q = 0; q < 9; ++q) atomicAdd(dweight + c * 9 + q, acc[q]);
-        if (dbias) atomicAdd(dbias + c, acc[9]);
-    }
 }
 
+__global__ void __launch_bounds__(kDwWarps *kWarp, 3) dwconv_silu_grad_kernel(const float *__restrict__ xin, const float *__restrict__ weight,
+                                                                             const float *__restrict__ dpre, float *__restrict__ dxin,
+                                                                             int64_t dx_cstride, float *__restrict__ dweight,
+                                                                             float *__restrict__ dbias, const DwGeom g) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int b, hc, cg, ws;
+    if (!dw_walk(g, (int64_t)blockIdx.x * kDwWarps + warp, b, hc, cg, ws)) return;
+    const int c = cg * kWarp + lane, w0 = ws * kDwC;
+    if (c >= g.C) return;
+    float wgt[9], acc[10];
+#pragma unroll
+    for (int q = 0; q < 9; ++q) wgt[q] = __ldg(weight + c * 9 + q);
+#pragma unroll
+    for (int q = 0; q < 10; ++q) acc[q] = 0.f;
+    const int h_begin = hc * g.rows_per_walk, h_end = min(g.H, h_begin + g.rows_per_walk);
+    if (w0 >= 1 && w0 + kDwC + 1 <= g.W) dw_grad_rows<true>(xin, dpre, wgt, dxin, dx_cstride, acc, g, b, c, h_begin, h_end, w0);
+    else dw_grad_rows<false>(xin, dpre, wgt, dxin, dx_cstride, acc, g, b, c, h_begin, h_end, w0);
+#pragma unroll
+    for (int q = 0; q < 9; ++q) atomicAdd(dweight + c * 9 + q, acc[q]);
+    if (dbias) atomicAdd(dbias + c, acc[9]);
+}
+
+// rows_per_walk: a multiple of 4, as long as possible (the 2-row halo of a walk is re-read) while >= ~48 warps per SM exist
 static int dw_geom(DwGeom &g, int64_t cstride, int64_t B, int64_t C, int64_t H, int64_t W, const void *cf_ptr) {
     if (B <= 0 || C <= 0 || H <= 0 || W <= 0 || cstride < C) return SS2D_EINVAL;
     g.B = (int)B; g.C = (int)C; g.H = (int)H; g.W = (int)W; g.cstride = cstride;
-    g.strips_w = (int)((W + kDwC - 1) / kDwC); g.strips_h = (int)((H + kDwR - 1) / kDwR); g.cgroups = (int)((C + kWarp - 1) / kWarp);
+    g.strips_w = (int)((W + kDwC - 1) / kDwC); g.cgroups = (int)((C + kWarp - 1) / kWarp);
     g.vec = W % 4 == 0 && (reinterpret_cast<uintptr_t>(cf_ptr) & 15) == 0;
-    g.hb_per_warp = 1;
-    if ((int64_t)g.strips_w * g.strips_h * g.cgroups * B / kDwWarps + 1 > 0x7fffffffLL) return SS2D_EINVAL;
+    const int64_t cols = (int64_t)g.strips_w * g.cgroups * B;
+    int64_t chunks = (148LL * 48 + cols - 1) / cols;
+    const int64_t max_chunks = (H + 3) / 4;
+    chunks = chunks < 1 ? 1 : (chunks > max_chunks ? max_chunks : chunks);
+    g.rows_per_walk = (int)(((H + chunks - 1) / chunks + 3) / 4 * 4);
+    g.hchunks = (int)((H + g.rows_per_walk - 1) / g.rows_per_walk);
+    if (cols * g.hchunks / kDwWarps + 1 > 0x7fffffffLL) return SS2D_EINVAL;
     return 0;
+}
+static unsigned dw_grid(const DwGeom &g) {
+    return (unsigned)(((int64_t)g.strips_w * g.cgroups * g.hchunks * g.B + kDwWarps - 1) / kDwWarps);
 }
 
 }  // namespace ss2d
@@ -221,9 +252,8 @@ extern "C" int ss2d_dwconv_silu_fwd(const float *xin, int64_t cstride, const flo
     if (!xin || !weight || !out) return SS2D_EINVAL;
     DwGeom g;
     if (int rc = dw_geom(g, cstride, batch, C, H, W, out)) return rc;
-    const int64_t strips = (int64_t)g.strips_w * g.strips_h * g.cgroups * batch;
-    dwconv_silu_fwd_kernel<<<(unsigned)((strips + kDwWarps - 1) / kDwWarps), kDwWarps * kWarp, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-        xin, weight, bias, out, g);
+    dwconv_silu_walk_kernel<kDwFwd><<<dw_grid(g), kDwWarps * kWarp, 0, reinterpret_cast<cudaStream_t>(stream)>>>(xin, weight, bias, out, nullptr,
+                                                                                                                 nullptr, g);
     return (int)cudaGetLastError();
 }
 
@@ -235,16 +265,7 @@ extern "C" int ss2d_dwconv_silu_bwd(const float *xin, int64_t cstride, const flo
     DwGeom g;
     if (int rc = dw_geom(g, cstride, batch, C, H, W, dout)) return rc;
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-    const int64_t strips = (int64_t)g.strips_w * g.strips_h * g.cgroups * batch;
-    dwconv_silu_dpre_kernel<<<(unsigned)((strips + kDwWarps - 1) / kDwWarps), kDwWarps * kWarp, 0, s>>>(xin, weight, bias, dout, dpre_scratch, g);
-    // row-blocks per warp in pass 2: as many as keeps >= ~8 warps per SM sub-partition in flight (fewer atomics per tap)
-    const int64_t want_warps = 148 * 4 * 8;
-    int64_t hbpw = strips / want_warps;
-    hbpw = hbpw < 1 ? 1 : (hbpw > g.strips_h ? g.strips_h : hbpw);
-    g.hb_per_warp = (int)hbpw;
-    const int64_t hchunks = (g.strips_h + hbpw - 1) / hbpw;
-    const int64_t walks = (int64_t)g.strips_w * g.cgroups * hchunks * batch;
-    dwconv_silu_grad_kernel<<<(unsigned)((walks + kDwWarps - 1) / kDwWarps), kDwWarps * kWarp, 0, s>>>(xin, weight, dpre_scratch, dxin, dx_cstride,
-                                                                                                       dweight, dbias, g);
+    dwconv_silu_walk_kernel<kDwDpre><<<dw_grid(g), kDwWarps * kWarp, 0, s>>>(xin, weight, bias, nullptr, dout, dpre_scratch, g);
+    dwconv_silu_grad_kernel<<<dw_grid(g), kDwWarps * kWarp, 0, s>>>(xin, weight, dpre_scratch, dxin, dx_cstride, dweight, dbias, g);
     return (int)cudaGetLastError();
 }
