@@ -26,7 +26,7 @@ __device__ __forceinline__ float warp_sum(float v) {
 
 // y:(B,D,L) -> out:(B,L,D);  out = (LN_D(y) * w + b) [* silu(z)]
 template <int NJ>
-__global__ void __launch_bounds__(kMnWarps *kWarp) merge_norm_fwd_kernel(const float *__restrict__ y, const float *__restrict__ w,
+__global__ void __launch_bounds__(kMnWarps *kWarp, NJ <= 8 ? 2 : 1) merge_norm_fwd_kernel(const float *__restrict__ y, const float *__restrict__ w,
                                                                          const float *__restrict__ bvec, const float *__restrict__ z,
                                                                          int64_t z_pstride, float *__restrict__ out, int D,
                                                                          int64_t L, float eps, int tiles_per_image) {
@@ -35,12 +35,41 @@ __global__ void __launch_bounds__(kMnWarps *kWarp) merge_norm_fwd_kernel(const f
     const int b = blockIdx.x / tiles_per_image;
     const int64_t l0 = (int64_t)(blockIdx.x % tiles_per_image) * kMnPix;
     const int nj = (D + kWarp - 1) / kWarp;
-    for (int d = warp; d < D; d += kMnWarps) {
+    constexpr int RPW = NJ * kWarp / kMnWarps;  // y rows per warp
+    constexpr int PPW = kMnPix / kMnWarps;      // pixels per warp
+    // every global load of the tile is issued before the first use: the RPW y rows of this warp, then (behind the barrier's
+    // back) the z values and the affine parameters of the PPW pixels this warp will normalise
+    {
+        float r[RPW];
         const int64_t l = l0 + lane;
-        tile[d * (kMnPix + 1) + lane] = l < L ? __ldg(y + ((int64_t)b * D + d) * L + l) : 0.f;
+#pragma unroll
+        for (int i = 0; i < RPW; ++i) {
+            const int d = warp + i * kMnWarps;
+            r[i] = (d < D && l < L) ? __ldg(y + ((int64_t)b * D + d) * L + l) : 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < RPW; ++i) {
+            const int d = warp + i * kMnWarps;
+            if (d < D) tile[d * (kMnPix + 1) + lane] = r[i];
+        }
+    }
+    float zv[PPW][NJ], wv[NJ], bv[NJ];
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+        const int d = lane + j * kWarp;
+        const bool ok = j < nj && d < D;
+        wv[j] = ok ? __ldg(w + d) : 0.f;
+        bv[j] = ok ? __ldg(bvec + d) : 0.f;
+#pragma unroll
+        for (int k = 0; k < PPW; ++k) {
+            const int64_t l = l0 + warp + k * kMnWarps;
+            zv[k][j] = (z && ok && l < L) ? __ldg(z + ((int64_t)b * L + l) * z_pstride + d) : 0.f;
+        }
     }
     __syncthreads();
-    for (int p = warp; p < kMnPix; p += kMnWarps) {
+#pragma unroll
+    for (int k = 0; k < PPW; ++k) {
+        const int p = warp + k * kMnWarps;
         const int64_t l = l0 + p;
         if (l >= L) break;
         float v[NJ];
@@ -61,13 +90,12 @@ __global__ void __launch_bounds__(kMnWarps *kWarp) merge_norm_fwd_kernel(const f
         }
         const float rstd = rsqrtf(warp_sum(q) / D + eps);
         float *o = out + ((int64_t)b * L + l) * D;
-        const float *zp = z ? z + ((int64_t)b * L + l) * z_pstride : nullptr;
 #pragma unroll
         for (int j = 0; j < NJ; ++j) {
             const int d = lane + j * kWarp;
             if (j < nj && d < D) {
-                float r = (v[j] - mean) * rstd * w[d] + bvec[d];
-                if (zp) { const float zv = zp[d]; r *= zv * sigmoidf_fast(zv); }
+                float r = (v[j] - mean) * rstd * wv[j] + bv[j];
+                if (z) r *= zv[k][j] * sigmoidf_fast(zv[k][j]);
                 o[d] = r;
             }
         }
@@ -76,7 +104,7 @@ __global__ void __launch_bounds__(kMnWarps *kWarp) merge_norm_fwd_kernel(const f
 
 // dout:(B,L,D) -> dy:(B,D,L), dz:(B,L,*) (z_pstride), dw, db (accumulated with atomics; zeroed by the caller)
 template <int NJ>
-__global__ void __launch_bounds__(kMnWarps *kWarp) merge_norm_bwd_kernel(const float *__restrict__ y, const float *__restrict__ w,
+__global__ void __launch_bounds__(kMnWarps *kWarp, NJ <= 8 ? 2 : 1) merge_norm_bwd_kernel(const float *__restrict__ y, const float *__restrict__ w,
                                                                          const float *__restrict__ bvec, const float *__restrict__ z,
                                                                          int64_t z_pstride, const float *__restrict__ dout,
                                                                          float *__restrict__ dy, float *__restrict__ dz,
@@ -95,14 +123,38 @@ __global__ void __launch_bounds__(kMnWarps *kWarp) merge_norm_bwd_kernel(const f
         const int64_t l0 = (tix % tiles_per_image) * kMnPix;
         const bool live = b < batch;  // the last block may run past the last tile
         __syncthreads();
-        if (live)
-            for (int d = warp; d < D; d += kMnWarps) {
-                const int64_t l = l0 + lane;
-                tile[d * (kMnPix + 1) + lane] = l < L ? __ldg(y + ((int64_t)b * D + d) * L + l) : 0.f;
+        constexpr int RPW = NJ * kWarp / kMnWarps, PPW = kMnPix / kMnWarps;
+        float gv[PPW][NJ], zv[PPW][NJ];  // dout / z of the pixels this warp owns: in flight across the barrier
+        if (live) {
+            float r[RPW];
+            const int64_t l = l0 + lane;
+#pragma unroll
+            for (int i = 0; i < RPW; ++i) {
+                const int d = warp + i * kMnWarps;
+                r[i] = (d < D && l < L) ? __ldg(y + ((int64_t)b * D + d) * L + l) : 0.f;
             }
+#pragma unroll
+            for (int k = 0; k < PPW; ++k) {
+                const int64_t lp = l0 + warp + k * kMnWarps;
+#pragma unroll
+                for (int j = 0; j < NJ; ++j) {
+                    const int d = lane + j * kWarp;
+                    const bool ok = j < nj && d < D && lp < L;
+                    gv[k][j] = ok ? __ldg(dout + ((int64_t)b * L + lp) * D + d) : 0.f;
+                    zv[k][j] = (z && ok) ? __ldg(z + ((int64_t)b * L + lp) * z_pstride + d) : 0.f;
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < RPW; ++i) {
+                const int d = warp + i * kMnWarps;
+                if (d < D) tile[d * (kMnPix + 1) + lane] = r[i];
+            }
+        }
         __syncthreads();
         if (live)
-            for (int p = warp; p < kMnPix; p += kMnWarps) {
+#pragma unroll
+            for (int k = 0; k < PPW; ++k) {
+                const int p = warp + k * kMnWarps;
                 const int64_t l = l0 + p;
                 if (l >= L) break;
                 float v[NJ];
@@ -122,8 +174,6 @@ __global__ void __launch_bounds__(kMnWarps *kWarp) merge_norm_bwd_kernel(const f
                     q = fmaf(c, c, q);
                 }
                 const float rstd = rsqrtf(warp_sum(q) / D + eps);
-                const float *go = dout + ((int64_t)b * L + l) * D;
-                const float *zp = z ? z + ((int64_t)b * L + l) * z_pstride : nullptr;
                 float *dzp = (z && dz) ? dz + ((int64_t)b * L + l) * dz_pstride : nullptr;
                 float s1 = 0.f, s2 = 0.f;
 #pragma unroll
@@ -131,11 +181,11 @@ __global__ void __launch_bounds__(kMnWarps *kWarp) merge_norm_bwd_kernel(const f
                     const int d = lane + j * kWarp;
                     if (j < nj && d < D) {
                         const float xh = (v[j] - mean) * rstd;
-                        float g = go[d];
-                        if (zp) {
-                            const float zv = zp[d], sg = sigmoidf_fast(zv);
-                            if (dzp) dzp[d] = g * (xh * w[d] + bvec[d]) * sg * (1.f + zv * (1.f - sg));
-                            g *= zv * sg;
+                        float g = gv[k][j];
+                        if (z) {
+                            const float zz = zv[k][j], sg = sigmoidf_fast(zz);
+                            if (dzp) dzp[d] = g * (xh * w[d] + bvec[d]) * sg * (1.f + zz * (1.f - sg));
+                            g *= zz * sg;
                         }
                         dw_acc[j] = fmaf(g, xh, dw_acc[j]);
                         db_acc[j] += g;
