@@ -81,3 +81,39 @@ def test_training_step_loss_and_every_gradient_match(ref_ready, fuse_block):
     gmax = max(float(g.abs().max()) for g in g_ref.values())
     worst = max((rel_err(g_ours[n], g_ref[n], floor=1e-2 * gmax), n) for n in g_ref)
     assert worst[0] < 1e-3, worst
+
+
+@pytest.mark.parametrize("force_fp32", [True, False], ids=["force_fp32", "native"])
+def test_cross_selective_scan_under_autocast_matches_reference(ref_ready, force_fp32):
+    """ADVICE (round 1): under torch.autocast the projections return 16-bit tensors; the reference then casts xs / dts /
+    Bs / Cs to float when force_fp32 is set (vmamba_layers.py:281-285; forward types v1 / v2 / v01) and scans in 16 bits
+    otherwise.  The drop-in must accept both and agree with the reference's own cross_selective_scan on the reference's
+    CUDA kernels (torch CrossScan / CrossMerge, SelectiveScanOflex) within the 16-bit gate."""
+    import sys
+    from focalnet_b200 import cross_selective_scan
+    vml = sys.modules["models.vmamba_layers"]
+    vml.selective_scan_cuda_oflex = sys.modules["selective_scan_cuda_oflex"]
+    torch.manual_seed(5)
+    B, D, H, W, N, R, K = 2, 64, 24, 32, 16, 4, 4
+    x = torch.randn(B, D, H, W, device="cuda")
+    xw = (torch.randn(K, R + 2 * N, D, device="cuda") * D ** -0.5).requires_grad_()
+    dtw = (torch.rand(K, D, R, device="cuda") * 2 - 1).requires_grad_()
+    dtb = (torch.rand(K, D, device="cuda") * 2 - 4).requires_grad_()
+    A_logs = torch.log(torch.arange(1, N + 1.0, device="cuda")).repeat(K * D, 1).requires_grad_()
+    Ds = torch.ones(K * D, device="cuda", requires_grad=True)
+    ln = torch.nn.LayerNorm(D).cuda()
+    dy = torch.randn(B, H, W, D, device="cuda")
+    res = []
+    for fn, extra in ((vml.cross_selective_scan, dict(SelectiveScan=vml.SelectiveScanOflex, CrossScan=vml.CrossScan, CrossMerge=vml.CrossMerge)),
+                      (cross_selective_scan, {})):
+        leaves = [t.detach().clone().requires_grad_() for t in (x, xw, dtw, dtb, A_logs, Ds)]
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            y = fn(leaves[0], leaves[1], None, leaves[2], leaves[3], leaves[4], leaves[5], delta_softplus=True, out_norm=ln,
+                   out_norm_shape="v0", force_fp32=force_fp32, no_einsum=True, **extra)
+        y.float().backward(dy)
+        res.append((y.float(), [t.grad for t in leaves]))
+        ln.zero_grad()
+    assert res[0][0].dtype == res[1][0].dtype
+    assert rel_err(res[1][0], res[0][0]) < 2e-2
+    for a, b, k in zip(res[1][1], res[0][1], ("dx", "dx_proj", "ddt_w", "ddt_b", "dA_logs", "dDs")):
+        assert rel_err(a, b) < 5e-2, k
