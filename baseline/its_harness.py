@@ -46,15 +46,21 @@ class _DeviceRewrite(torch.overrides.TorchFunctionMode):
         return func(*args, **kwargs)
 
 
-def _ref_cuda_module():
-    """The reference's own oflex CUDA extension rebuilt for sm_100a (oracle/build_ref.sh), or None."""
-    so = os.path.join(ROOT, "oracle", "_ref", "selective_scan_cuda_oflex_ref.so")
-    if not (os.path.exists(so) and torch.cuda.is_available()):
-        return None
-    spec = importlib.util.spec_from_file_location("selective_scan_cuda_oflex_ref", so)
-    mod = importlib.util.module_from_spec(spec)
-    spec.loader.exec_module(mod)
-    return mod
+_REF_CUDA = None
+
+
+def ref_cuda_module():
+    """The reference's own oflex CUDA extension rebuilt for sm_100a (oracle/build_ref.sh), or None.  Loaded under its own
+    name and cached here: `sys.modules["selective_scan_cuda_oflex"]` may hold this library's drop-in of the same name."""
+    global _REF_CUDA
+    if _REF_CUDA is None:
+        so = os.path.join(ROOT, "oracle", "_ref", "selective_scan_cuda_oflex_ref.so")
+        if not (os.path.exists(so) and torch.cuda.is_available()):
+            return None
+        spec = importlib.util.spec_from_file_location("selective_scan_cuda_oflex_ref", so)
+        _REF_CUDA = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(_REF_CUDA)
+    return _REF_CUDA
 
 
 _models = {}
@@ -74,10 +80,6 @@ def import_reference(variant: str = "g2"):
                 sys.path.append(STUBS)
     if ITS_REF not in sys.path:
         sys.path.insert(0, ITS_REF)
-    if "selective_scan_cuda_oflex" not in sys.modules:
-        ref = _ref_cuda_module()  # vmamba_layers.py:74-79 imports it by name (and swallows a failure)
-        if ref is not None:
-            sys.modules["selective_scan_cuda_oflex"] = ref
     mod = importlib.import_module("models.MIMOUNet" if variant == "g2" else "models.MIMOUNet_g4")
     _models[variant] = mod
     return mod
@@ -125,9 +127,10 @@ def bind_reference_cuda(model, triton_cross: bool = True) -> int:
     """The reference arm on the GPU: SelectiveScanOflex on the reference's own CUDA kernels (oracle/_ref) with the shipped
     Triton CrossScan / CrossMerge (forward type v4, vmamba_layers.py:447) or their torch twins (:29-71)."""
     vml = sys.modules["models.vmamba_layers"]
-    if "selective_scan_cuda_oflex" not in sys.modules:
+    ref = ref_cuda_module()
+    if ref is None:
         raise RuntimeError("oracle/_ref/selective_scan_cuda_oflex_ref.so is not built")
-    vml.selective_scan_cuda_oflex = sys.modules["selective_scan_cuda_oflex"]
+    vml.selective_scan_cuda_oflex = ref  # the name SelectiveScanOflex.forward / .backward resolve (vmamba_layers.py:183,193)
     n = 0
     for m in ss2d_modules(model):
         kw = dict(force_fp32=False, SelectiveScan=vml.SelectiveScanOflex, no_einsum=True)

@@ -31,8 +31,7 @@ def _bind_reference(model):
 @pytest.fixture(scope="module")
 def ref_ready():
     H.import_reference("g2")
-    import sys
-    if "selective_scan_cuda_oflex" not in sys.modules:
+    if H.ref_cuda_module() is None:
         pytest.skip("oracle/_ref not built")
 
 
@@ -92,17 +91,18 @@ def test_cross_selective_scan_under_autocast_matches_reference(ref_ready, force_
     import sys
     from focalnet_b200 import cross_selective_scan
     vml = sys.modules["models.vmamba_layers"]
-    vml.selective_scan_cuda_oflex = sys.modules["selective_scan_cuda_oflex"]
+    vml.selective_scan_cuda_oflex = H.ref_cuda_module()
     torch.manual_seed(5)
-    B, D, H, W, N, R, K = 2, 64, 24, 32, 16, 4, 4
-    x = torch.randn(B, D, H, W, device="cuda")
+    B, D, Hh, W, N, R, K = 2, 64, 24, 32, 16, 4, 4
+    # inside an autocast region x arrives from the depthwise conv in 16 bits; force_fp32 modules see whatever comes
+    x = torch.randn(B, D, Hh, W, device="cuda").to(torch.float32 if force_fp32 else torch.bfloat16)
     xw = (torch.randn(K, R + 2 * N, D, device="cuda") * D ** -0.5).requires_grad_()
     dtw = (torch.rand(K, D, R, device="cuda") * 2 - 1).requires_grad_()
     dtb = (torch.rand(K, D, device="cuda") * 2 - 4).requires_grad_()
     A_logs = torch.log(torch.arange(1, N + 1.0, device="cuda")).repeat(K * D, 1).requires_grad_()
     Ds = torch.ones(K * D, device="cuda", requires_grad=True)
     ln = torch.nn.LayerNorm(D).cuda()
-    dy = torch.randn(B, H, W, D, device="cuda")
+    dy = torch.randn(B, Hh, W, D, device="cuda")
     res = []
     for fn, extra in ((vml.cross_selective_scan, dict(SelectiveScan=vml.SelectiveScanOflex, CrossScan=vml.CrossScan, CrossMerge=vml.CrossMerge)),
                       (cross_selective_scan, {})):

@@ -157,6 +157,8 @@ def test_dropin_modules_have_reference_signatures():
         assert tuple(xs.shape) == (1, 4, 2, 24)
     finally:
         sys.path.pop(0)
+        for m in ("selective_scan_cuda_oflex", "selective_scan_cuda_core", "csm_triton"):
+            sys.modules.pop(m, None)  # later tests bind the reference's own extension under the first of these names
 
 
 def test_full_ss2d_block_matches_torch_composition():
