@@ -1,5 +1,5 @@
-"""Times the S1 scan kernels only (fwd, bwd) with CUDA events over back-to-back launches; SS2D_SCAN_IMPL=warpscan
-in the environment selects the general warp-scan kernels for an A/B comparison."""
+"""Times the S1 scan kernels only (fwd, bwd) with CUDA events over back-to-back launches; `warpscan` / `statelanes` on the
+command line pins the kernel family (test hook ss2d_set_default_family) for an A/B comparison; `s3` adds the fused seam."""
 import json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -19,7 +19,10 @@ peak = json.load(open("MEASURED_PEAKS.json"))["hbm_gbs"] if os.path.exists("MEAS
 shapes = [(8, 192, 64, 64, "micro"), (32, 192, 128, 128, "train-L16384"), (32, 192, 32, 32, "train-L1024"), (1, 192, 120, 160, "fullres-g4")]
 if len(sys.argv) > 1 and sys.argv[1] == "micro":
     shapes = shapes[:1]
-print("impl:", os.environ.get("SS2D_SCAN_IMPL", "default"))
+from focalnet_b200 import _lib
+fam = _lib.FAMILY_WARPSCAN if "warpscan" in sys.argv else (_lib.FAMILY_STATELANES if "statelanes" in sys.argv else 0)
+_lib.lib().ss2d_set_default_family(fam)
+print("family:", {0: "auto (by problem size)", 1: "statelanes", 2: "warpscan"}[fam])
 for (B, D, H, W, tag) in shapes:
     K, N, L = 4, 16, H * W
     for dt, es in ((torch.float32, 4), (torch.bfloat16, 2)):
