@@ -52,7 +52,7 @@ class CrossBwdParams(C.Structure):
 
 
 EXPORTS = ("ss2d_abi_version", "ss2d_build_info", "ss2d_error_string", "ss2d_scan_ckpt_floats", "ss2d_cross_work_floats",
-           "ss2d_scan_family", "ss2d_set_default_family", "ss2d_cross_family", "ss2d_optim_partials", "ss2d_optim_clip_adam",
+           "ss2d_scan_family", "ss2d_set_default_family", "ss2d_cross_family", "ss2d_optim_partials", "ss2d_optim_clip_adam", "ss2d_dt_proj_fwd", "ss2d_dt_proj_bwd",
            "ss2d_plane_transpose", "ss2d_selective_scan_fwd",
            "ss2d_selective_scan_bwd", "ss2d_cross_scan", "ss2d_cross_merge", "ss2d_cross_scan_fwd",
            "ss2d_cross_scan_bwd", "ss2d_dwconv_silu_fwd", "ss2d_dwconv_silu_bwd", "ss2d_merge_norm_gate_fwd",
@@ -96,6 +96,8 @@ def lib():
         sigs["ss2d_dwconv_silu_bwd"] = [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _i64, _i64, _i64, _i64, _vp]
         sigs["ss2d_plane_transpose"] = [_vp, _vp, _i64, _i64, _i64, _i32, _vp]
         sigs["ss2d_cross_permute"] = [_vp, _vp, _i64, _i64, _i64, _i64, _i32, _i32, _vp]
+        sigs["ss2d_dt_proj_fwd"] = [_vp, _i64, _i64, _i64, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _vp]
+        sigs["ss2d_dt_proj_bwd"] = [_vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _vp]
         _f32 = C.c_float
         sigs["ss2d_merge_norm_gate_fwd"] = [_vp, _vp, _vp, _f32, _vp, _i64, _vp, _i64, _i64, _i64, _vp]
         sigs["ss2d_merge_norm_gate_bwd"] = [_vp, _vp, _vp, _f32, _vp, _i64, _vp, _vp, _vp, _i64, _vp, _vp, _i64, _i64, _i64, _vp]

@@ -305,6 +305,56 @@ def _to_scan_order(t: torch.Tensor, H: int, W: int) -> torch.Tensor:
     return ToScanOrderFn.apply(t, H, W)
 
 
+class DtProjFn(torch.autograd.Function):
+    """dts_lr (B,K,R,L) fp32 (any batch / direction / rank strides, unit stride along L), W (K,D,R)  ->  (B, K*D, L):
+    the low-rank dt projection ``F.conv1d(dts.view(B, K*R, L), W.view(K*D, R, 1), groups=K)`` of vmamba_layers.py:264 as one
+    HBM stream each way (ss2d_dt_proj_fwd/_bwd) instead of a grouped cuDNN convolution with layout conversions."""
+
+    @staticmethod
+    def supported(dts_lr, W):
+        B, K, R, L = dts_lr.shape
+        return (dts_lr.is_cuda and dts_lr.dtype == torch.float32 and W.dtype == torch.float32 and not torch.is_autocast_enabled()
+                and R <= 8 and W.shape[1] <= 512 and L % 4 == 0 and dts_lr.stride(3) == 1 and dts_lr.data_ptr() % 16 == 0
+                and all(st % 4 == 0 for st in dts_lr.stride()[:3]))
+
+    @staticmethod
+    def forward(ctx, dts_lr, W):
+        B, K, R, L = dts_lr.shape
+        D = W.shape[1]
+        Wc = W.contiguous()
+        out = torch.empty((B, K * D, L), device=dts_lr.device, dtype=torch.float32)
+        with torch.cuda.device(dts_lr.device):
+            _lib.check(_lib.lib().ss2d_dt_proj_fwd(dts_lr.data_ptr(), dts_lr.stride(0), dts_lr.stride(1), dts_lr.stride(2), Wc.data_ptr(),
+                                                   out.data_ptr(), B, K, D, R, L, _stream(dts_lr)), "ss2d_dt_proj_fwd")
+        ctx.save_for_backward(dts_lr, Wc)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        dts_lr, Wc = ctx.saved_tensors
+        B, K, R, L = dts_lr.shape
+        D = Wc.shape[1]
+        dout = dout.contiguous()
+        dx = torch.empty((B, K, R, L), device=dout.device, dtype=torch.float32)
+        dW = torch.zeros_like(Wc)
+        with torch.cuda.device(dout.device):
+            _lib.check(_lib.lib().ss2d_dt_proj_bwd(dout.data_ptr(), dts_lr.data_ptr(), dts_lr.stride(0), dts_lr.stride(1), dts_lr.stride(2),
+                                                   Wc.data_ptr(), dx.data_ptr(), dW.data_ptr(), B, K, D, R, L, _stream(dout)),
+                       "ss2d_dt_proj_bwd")
+        return dx, dW
+
+
+def _dt_proj(dts_lr, dt_projs_weight, no_einsum=True):
+    """(B,K,R,L) x (K,D,R) -> (B, K*D, L).  fp32 outside autocast: this library's stream kernels (exact fp32 — the library
+    conv1d would round to TF32 under torch's default cuDNN policy); otherwise the reference's own library call."""
+    B, K, R, L = dts_lr.shape
+    if DtProjFn.supported(dts_lr, dt_projs_weight):
+        return DtProjFn.apply(dts_lr, dt_projs_weight)
+    if no_einsum:
+        return F.conv1d(dts_lr.reshape(B, K * R, L), dt_projs_weight.reshape(-1, R, 1), groups=K)
+    return torch.einsum("b k r l, k d r -> b k d l", dts_lr, dt_projs_weight).reshape(B, -1, L)
+
+
 def cross_selective_scan(
     x: torch.Tensor = None,
     x_proj_weight: torch.Tensor = None,
@@ -354,10 +404,7 @@ def cross_selective_scan(
             x_dbl = x_dbl + x_proj_bias.reshape(1, -1, 1)
     x_dbl = _to_scan_order(x_dbl.view(B, K, R + 2 * N, L), H, W)        # (B, K, R+2N, L), each direction's scan order
     dts_lr, Bs, Cs = torch.split(x_dbl, [R, N, N], dim=2)
-    if no_einsum:
-        dts = F.conv1d(dts_lr.reshape(B, K * R, L), dt_projs_weight.reshape(K * D, R, 1), groups=K)
-    else:
-        dts = torch.einsum("b k r l, k d r -> b k d l", dts_lr, dt_projs_weight).reshape(B, K * D, L)
+    dts = _dt_proj(dts_lr, dt_projs_weight, no_einsum)
     As = -torch.exp(A_logs.to(torch.float))
     xin = x
     if force_fp32:  # vmamba_layers.py:281-285
@@ -423,7 +470,7 @@ def ss2d_forward(m: torch.nn.Module, x: torch.Tensor) -> torch.Tensor:
     x_dbl = F.conv1d(xc.reshape(B, D, L), m.x_proj_weight.reshape(K * (R + 2 * N), D, 1))  # the reference's library call
     x_dbl = _to_scan_order(x_dbl.view(B, K, R + 2 * N, L), H, W)
     dts_lr, Bs, Cs = torch.split(x_dbl, [R, N, N], dim=2)
-    dts = F.conv1d(dts_lr.reshape(B, K * R, L), m.dt_projs_weight.reshape(K * D, R, 1), groups=K)
+    dts = _dt_proj(dts_lr, m.dt_projs_weight)
     y = FusedCrossScanFn.apply(xc, dts, -torch.exp(m.A_logs.float()), Bs, Cs, m.Ds.float(), m.dt_projs_bias.reshape(-1).float(), True)
     y = merge_norm_gate(y, m.out_norm.weight, m.out_norm.bias, m.out_norm.eps, z=zh).view(B, H, W, D)
     return m.dropout(m.out_proj(y))

@@ -231,6 +231,20 @@ int ss2d_merge_norm_gate_bwd(const float *y, const float *weight, const float *b
                              float *dweight, float *dbias, int64_t batch, int64_t D, int64_t L, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * low-rank dt projection of the SS2D core (first half of SURVEY §8f row N2): replaces
+ *     dts = F.conv1d(dts.contiguous().view(B, -1, L), dt_projs_weight.view(K * D, -1, 1), groups=K)
+ * of cross_selective_scan (ITS/models/vmamba_layers.py:264; einsum twin :270) and its backward, as plain HBM streams.
+ *   dtlr : f32, element (b, k, r, l) at dtlr + b*sb + k*sk + r*sr + l  (the dt rows of the permuted x_dbl; no copy)
+ *   W    : (K, D, R) f32 = dt_projs_weight ; out / dout : (B, K*D, L) f32 contiguous ; R <= 8, D <= 512
+ *   bwd  : d_dtlr (B, K, R, L) f32 contiguous, written ; dW (K, D, R) f32 ZEROED (accumulated)
+ * L % 4 == 0 and 16-byte aligned rows are required (SS2D_ESTRIDE otherwise: the caller keeps the library conv).
+ * ------------------------------------------------------------------------------------------- */
+int ss2d_dt_proj_fwd(const float *dtlr, int64_t sb, int64_t sk, int64_t sr, const float *W, float *out, int64_t B, int64_t K,
+                     int64_t D, int64_t R, int64_t L, void *stream);
+int ss2d_dt_proj_bwd(const float *dout, const float *dtlr, int64_t sb, int64_t sk, int64_t sr, const float *W, float *d_dtlr,
+                     float *dW, int64_t B, int64_t K, int64_t D, int64_t R, int64_t L, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
  * optimizer side of the data-parallel training step: global-norm clip + Adam + zero-grad over ONE
  * flat fp32 bucket, two launches.  Replaces clip_grad_norm_(params, 0.001); optimizer.step(); optimizer.zero_grad()
  * of ITS/train.py:61,89-91 (Adam(lr, betas=(0.9, 0.999), eps=1e-8), train.py:16).

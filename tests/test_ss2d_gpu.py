@@ -316,3 +316,26 @@ def test_plane_transpose_and_accumulate(shape):
     ref = acc + src.transpose(1, 2)
     _lib.check(_lib.lib().ss2d_plane_transpose(src.data_ptr(), acc.data_ptr(), P, H, W, 1, st), "ss2d_plane_transpose")
     assert torch.equal(acc, ref)
+
+
+@pytest.mark.parametrize("shape", [(2, 4, 6, 4096, 192), (1, 4, 1, 100, 32), (3, 4, 8, 1200, 48), (8, 4, 6, 64, 192)],
+                         ids=lambda s: "x".join(map(str, s)))
+def test_dt_proj_matches_library_grouped_conv(shape):
+    """ss2d_dt_proj_fwd/_bwd == F.conv1d(dts.view(B, K*R, L), W.view(K*D, R, 1), groups=K) (vmamba_layers.py:264) in fp64,
+    fed with the strided dt rows of an x_dbl-shaped tensor (no .contiguous() copy)."""
+    from focalnet_b200.ss2d import DtProjFn
+    B, K, R, L, D = shape
+    g = torch.Generator().manual_seed(L + R)
+    x_dbl = torch.randn(B, K, R + 32, L, generator=g).cuda().requires_grad_()
+    W = (torch.rand(K, D, R, generator=g) * 2 - 1).cuda().requires_grad_()
+    dout = torch.randn(B, K * D, L, generator=g).cuda()
+    dts_lr = x_dbl[:, :, :R]
+    assert not dts_lr.is_contiguous() and DtProjFn.supported(dts_lr, W)
+    out = DtProjFn.apply(dts_lr, W)
+    out.backward(dout)
+    xr, Wr = x_dbl.detach().double().requires_grad_(), W.detach().double().requires_grad_()
+    ref = torch.nn.functional.conv1d(xr[:, :, :R].reshape(B, K * R, L), Wr.reshape(K * D, R, 1), groups=K)
+    ref.backward(dout.double())
+    assert rel_err(out, ref) < 1e-6
+    assert rel_err(x_dbl.grad, xr.grad) < 1e-5 and rel_err(W.grad, Wr.grad) < 1e-5
+    assert not DtProjFn.supported(x_dbl[:, :, :R, 1:], W)   # unaligned rows: the library call keeps that case
