@@ -74,3 +74,23 @@ for (B, D, H, W, tag) in [(8, 192, 64, 64, "micro"), (32, 192, 128, 128, "train-
     def mb():
         o = merge_norm_gate(ym, lw, lb, 1e-5, z=zz); torch.autograd.grad(o, (ym, lw, lb, zz), go)
     rep(f"[{tag} float32] merge+LayerNorm+gate fwd+bwd", timeit(mb, n=10), 12 * B * D * L + 20 * B * D * L)
+    # the two projections of the fused core (vmamba_layers.py:262-264): library calls vs this library's dt_proj stream kernels
+    import torch.nn.functional as Fn
+    from focalnet_b200.ss2d import DtProjFn
+    R = 6
+    xc = torch.randn(B, D, L).cuda()
+    Wx = torch.randn(K * (R + 2 * N), D, 1).cuda() * D ** -0.5
+    rep(f"[{tag} float32] x_proj as conv1d (cuDNN, TF32 default)", timeit(lambda: Fn.conv1d(xc, Wx)), 4 * (B * D * L + B * K * (R + 2 * N) * L))
+    rep(f"[{tag} float32] x_proj as matmul (cuBLAS fp32)", timeit(lambda: torch.matmul(Wx[:, :, 0], xc)), 4 * (B * D * L + B * K * (R + 2 * N) * L))
+    xd = torch.randn(B, K, R + 2 * N, L).cuda().requires_grad_()
+    Wd = torch.randn(K, D, R).cuda().requires_grad_()
+    gd = torch.randn(B, K * D, L).cuda()
+    rep(f"[{tag} float32] dt_proj fwd (ss2d_dt_proj_fwd)", timeit(lambda: DtProjFn.apply(xd.detach()[:, :, :R], Wd.detach())), 4 * B * K * L * (R + D))
+    rep(f"[{tag} float32] dt_proj fwd, library grouped conv1d", timeit(lambda: Fn.conv1d(xd.detach()[:, :, :R].reshape(B, K * R, L), Wd.detach().reshape(K * D, R, 1), groups=K)), 4 * B * K * L * (R + D))
+    def dtb(ours):
+        o = DtProjFn.apply(xd[:, :, :R], Wd) if ours else Fn.conv1d(xd[:, :, :R].reshape(B, K * R, L), Wd.reshape(K * D, R, 1), groups=K)
+        torch.autograd.grad(o, (xd, Wd), gd)
+    rep(f"[{tag} float32] dt_proj fwd+bwd (ours, autograd)", timeit(lambda: dtb(True), n=10), 4 * B * K * L * (3 * D + 3 * R))
+    rep(f"[{tag} float32] dt_proj fwd+bwd (library conv1d, autograd)", timeit(lambda: dtb(False), n=10), 4 * B * K * L * (3 * D + 3 * R))
+    del xc, xd, gd
+    torch.cuda.empty_cache()
