@@ -99,47 +99,45 @@ __device__ __forceinline__ void dw_walk_rows(const float *__restrict__ xin, cons
                                              const float *__restrict__ dout, float *__restrict__ dpre, const DwGeom &g, int b, int c,
                                              int h_begin, int h_end, int w0) {
     const float *img = xin + (int64_t)b * g.H * g.W * g.cstride + c;
-    // rows h-1, h, h+1 live in r0, r1, r2; every iteration puts rows h+2 and h+3 in flight (20 independent 128-byte loads
-    // per warp) and evaluates rows h and h+1 meanwhile; the compiler resolves the rotation by renaming (unroll 3)
-    float r0[kDwWin], r1[kDwWin], r2[kDwWin], n0[kDwWin], n1[kDwWin];
-    dw_load_row<INTERIOR>(r0, img, g.cstride, h_begin - 1, g.H, g.W, w0);
-    dw_load_row<INTERIOR>(r1, img, g.cstride, h_begin, g.H, g.W, w0);
-    dw_load_row<INTERIOR>(r2, img, g.cstride, h_begin + 1, g.H, g.W, w0);
-    auto emit = [&](int h, const float (&ra)[kDwWin], const float (&rb)[kDwWin], const float (&rc)[kDwWin]) {
-        const int64_t cf_off = (((int64_t)b * g.C + c) * g.H + h) * g.W + w0;
-        if constexpr (MODE == kDwFwd) {
-            float o[kDwC];
+    float win[4][kDwWin];
+    // h_begin is a multiple of 4 (rows_per_walk is): row h lives in buffer h & 3, all buffer indices are compile-time constants
+    dw_load_row<INTERIOR>(win[3], img, g.cstride, h_begin - 1, g.H, g.W, w0);
+    dw_load_row<INTERIOR>(win[0], img, g.cstride, h_begin, g.H, g.W, w0);
+    dw_load_row<INTERIOR>(win[1], img, g.cstride, h_begin + 1, g.H, g.W, w0);
+#pragma unroll 1
+    for (int h4 = h_begin; h4 < h_end; h4 += 4) {
 #pragma unroll
-            for (int j = 0; j < kDwC; ++j) {
-                const float s = dw_conv_at(wgt, bv, ra, rb, rc, j);
-                o[j] = s * sigmoidf_fast(s);
-            }
-            dw_row_store(out + cf_off, o, g.W - w0, g.vec);
-        } else {
-            float go[kDwC];
-            dw_row_load(go, dout + cf_off, g.W - w0, g.vec);
-            float *drow = dpre + (((int64_t)b * g.H + h) * g.W + w0) * g.C + c;
+        for (int k = 0; k < 4; ++k) {
+            const int h = h4 + k;
+            if (h >= h_end) break;
+            dw_load_row<INTERIOR>(win[(k + 2) & 3], img, g.cstride, h + 2, g.H, g.W, w0);  // in flight while row h is evaluated
+            float (&ra)[kDwWin] = win[(k + 3) & 3], (&rb)[kDwWin] = win[k], (&rc)[kDwWin] = win[(k + 1) & 3];
+            const int64_t cf_off = (((int64_t)b * g.C + c) * g.H + h) * g.W + w0;
+            if constexpr (MODE == kDwFwd) {
+                float o[kDwC];
 #pragma unroll
-            for (int j = 0; j < kDwC; ++j) {
-                const float s = dw_conv_at(wgt, bv, ra, rb, rc, j);
-                const float sg = sigmoidf_fast(s);
-                if (INTERIOR || w0 + j < g.W) drow[(int64_t)j * g.C] = go[j] * sg * (1.f + s * (1.f - sg));
+                for (int j = 0; j < kDwC; ++j) {
+                    const float s = dw_conv_at(wgt, bv, ra, rb, rc, j);
+                    o[j] = s * sigmoidf_fast(s);
+                }
+                dw_row_store(out + cf_off, o, g.W - w0, g.vec);
+            } else {
+                float go[kDwC];
+                dw_row_load(go, dout + cf_off, g.W - w0, g.vec);
+                float *drow = dpre + (((int64_t)b * g.H + h) * g.W + w0) * g.C + c;
+#pragma unroll
+                for (int j = 0; j < kDwC; ++j) {
+                    const float s = dw_conv_at(wgt, bv, ra, rb, rc, j);
+                    const float sg = sigmoidf_fast(s);
+                    if (INTERIOR || w0 + j < g.W) drow[(int64_t)j * g.C] = go[j] * sg * (1.f + s * (1.f - sg));
+                }
             }
         }
-    };
-#pragma unroll 3
-    for (int h = h_begin; h < h_end; h += 2) {
-        dw_load_row<INTERIOR>(n0, img, g.cstride, h + 2, g.H, g.W, w0);
-        dw_load_row<INTERIOR>(n1, img, g.cstride, h + 3, g.H, g.W, w0);
-        emit(h, r0, r1, r2);
-        if (h + 1 < h_end) emit(h + 1, r1, r2, n0);
-#pragma unroll
-        for (int j = 0; j < kDwWin; ++j) { r0[j] = r2[j]; r1[j] = n0[j]; r2[j] = n1[j]; }
     }
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(kDwWarps *kWarp, 4) dwconv_silu_walk_kernel(const float *__restrict__ xin, const float *__restrict__ weight,
+__global__ void __launch_bounds__(kDwWarps *kWarp, 5) dwconv_silu_walk_kernel(const float *__restrict__ xin, const float *__restrict__ weight,
                                                                              const float *__restrict__ bias, float *__restrict__ out,
                                                                              const float *__restrict__ dout, float *__restrict__ dpre,
                                                                              const DwGeom g) {
