@@ -9,8 +9,8 @@
 //   fwd : one pass, every thread owns 4 consecutive steps (128-bit accesses), keeps the R low-rank rows in registers and
 //         streams the D output rows of its slice; W of the direction sits in shared memory.  Bytes: 4*B*K*L*(R + D).
 //   bwd : ddelta is read twice — once for d_dtlr[b,k,r,l] = sum_d W[k,d,r] ddelta[b,k*D+d,l] (same thread mapping, R
-//         128-bit accumulators per thread) and once for dW[k,d,r] = sum_{b,l} ddelta * dtlr (a warp per (k, d, batch
-//         row), lanes across l, one atomicAdd per (k,d,r) and warp).  Bytes: 4*B*K*L*(2*D + 2*R).
+//         128-bit accumulators per thread) and once for dW[k,d,r] = sum_{b,l} ddelta * dtlr (a warp per (batch row, k, 4 consecutive
+//         d), lanes across l, one atomicAdd per (k,d,r) and warp).  Bytes: 4*B*K*L*(2*D + 2*R).
 // `dtlr` is addressed through element strides so that it can be the dt rows of the permuted x_dbl (no .contiguous() copy).
 #include "ss2d_common.cuh"
 #include "../../include/ss2d_b200.h"
@@ -80,35 +80,51 @@ __global__ void __launch_bounds__(kDtThreads) dt_proj_bwd_x_kernel(const float *
     for (int r = 0; r < R; ++r) *reinterpret_cast<float4 *>(dx + (((int64_t)b * g.K + k) * R + r) * g.L + l) = acc[r];
 }
 
-// dW[k, d, r] += sum_l dout[b, k*D + d, l] * dtlr[b, k, r, l]   — one warp per (b, k, d) row, lanes across l
+// dW[k, d, r] += sum_l dout[b, k*D + d, l] * dtlr[b, k, r, l]   — one warp per (b, k, kDtRows consecutive d), lanes across l:
+// the R low-rank rows are loaded once per kDtRows rows of dout (they come from L1 / L2: 192 rows of a direction share them)
+constexpr int kDtRows = 4;
 template <int R>
 __global__ void __launch_bounds__(kDtThreads) dt_proj_bwd_w_kernel(const float *__restrict__ dout, const float *__restrict__ dtlr,
                                                                   float *__restrict__ dW, const DtGeom g) {
     const int lane = threadIdx.x & 31;
-    const int64_t row = (int64_t)blockIdx.x * (kDtThreads / kWarp) + (threadIdx.x >> 5);  // (b, k, d)
-    if (row >= g.B * g.K * g.D) return;
-    const int d = (int)(row % g.D), k = (int)((row / g.D) % g.K), b = (int)(row / (g.D * g.K));
-    const float *gp = dout + row * g.L;
+    const int64_t dgroups = (g.D + kDtRows - 1) / kDtRows;
+    const int64_t unit = (int64_t)blockIdx.x * (kDtThreads / kWarp) + (threadIdx.x >> 5);  // (b, k, d group)
+    if (unit >= g.B * g.K * dgroups) return;
+    const int d0 = (int)(unit % dgroups) * kDtRows, k = (int)((unit / dgroups) % g.K), b = (int)(unit / (dgroups * g.K));
+    const float *gp = dout + (((int64_t)b * g.K + k) * g.D + d0) * g.L;
     const float *xp = dtlr + b * g.sb + k * g.sk;
-    float acc[R];
+    float acc[kDtRows][R];
 #pragma unroll
-    for (int r = 0; r < R; ++r) acc[r] = 0.f;
+    for (int i = 0; i < kDtRows; ++i)
+#pragma unroll
+        for (int r = 0; r < R; ++r) acc[i][r] = 0.f;
     for (int64_t l = lane * 4; l < g.L; l += kWarp * 4) {
-        const float4 v = __ldg(reinterpret_cast<const float4 *>(gp + l));
+        float4 v[kDtRows];
+#pragma unroll
+        for (int i = 0; i < kDtRows; ++i)
+            v[i] = d0 + i < g.D ? __ldg(reinterpret_cast<const float4 *>(gp + (int64_t)i * g.L + l)) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             const float4 x = __ldg(reinterpret_cast<const float4 *>(xp + r * g.sr + l));
-            acc[r] = fmaf(v.x, x.x, fmaf(v.y, x.y, fmaf(v.z, x.z, fmaf(v.w, x.w, acc[r]))));
+#pragma unroll
+            for (int i = 0; i < kDtRows; ++i)
+                acc[i][r] = fmaf(v[i].x, x.x, fmaf(v[i].y, x.y, fmaf(v[i].z, x.z, fmaf(v[i].w, x.w, acc[i][r]))));
         }
     }
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
+    for (int i = 0; i < kDtRows; ++i)
 #pragma unroll
-        for (int m = 16; m >= 1; m >>= 1) acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], m);
-    }
+        for (int r = 0; r < R; ++r) {
+#pragma unroll
+            for (int m = 16; m >= 1; m >>= 1) acc[i][r] += __shfl_xor_sync(0xffffffffu, acc[i][r], m);
+        }
     if (lane == 0) {
 #pragma unroll
-        for (int r = 0; r < R; ++r) atomicAdd(dW + ((int64_t)k * g.D + d) * R + r, acc[r]);
+        for (int i = 0; i < kDtRows; ++i)
+            if (d0 + i < g.D) {
+#pragma unroll
+                for (int r = 0; r < R; ++r) atomicAdd(dW + ((int64_t)k * g.D + d0 + i) * R + r, acc[i][r]);
+            }
     }
 }
 
@@ -136,8 +152,8 @@ template <int R> static int dt_fwd_t(const float *dtlr, const float *W, float *o
 template <int R> static int dt_bwd_t(const float *dout, const float *dtlr, const float *W, float *dx, float *dW, DtGeom g, cudaStream_t s) {
     const int64_t ltiles = (g.L / 4 + kDtThreads - 1) / kDtThreads;
     dt_proj_bwd_x_kernel<R><<<dim3((unsigned)ltiles, (unsigned)g.K, (unsigned)g.B), kDtThreads, g.D * R * sizeof(float), s>>>(dout, W, dx, g);
-    const int64_t rows = g.B * g.K * g.D, wpb = kDtThreads / kWarp;
-    dt_proj_bwd_w_kernel<R><<<(unsigned)((rows + wpb - 1) / wpb), kDtThreads, 0, s>>>(dout, dtlr, dW, g);
+    const int64_t units = g.B * g.K * ((g.D + kDtRows - 1) / kDtRows), wpb = kDtThreads / kWarp;
+    dt_proj_bwd_w_kernel<R><<<(unsigned)((units + wpb - 1) / wpb), kDtThreads, 0, s>>>(dout, dtlr, dW, g);
     return (int)cudaGetLastError();
 }
 
