@@ -196,7 +196,7 @@ static int cross_dispatch(bool merge, const void *in, void *out, int64_t B, int6
 // src: planes of (H, W) -> dst: planes of (W, H), dst = src^T or dst += src^T.  The fused seam on the state-lanes
 // kernels walks directions 1 / 3 over x^T (and accumulates their outputs into y^T), so that every direction reads and
 // writes CONTIGUOUS runs: one transposed copy of the 192-row x, not the reference's 4x (B,4,D,L) tensor.
-template <bool ACC>
+template <bool ACC, bool VEC>
 __global__ void __launch_bounds__(kTile *kRows) plane_transpose_kernel(const float *__restrict__ src, float *__restrict__ dst, int H, int W) {
     __shared__ float tile[kTile][kTile + 1];
     const int tiles_w = (W + kTile - 1) / kTile, tiles_h = (H + kTile - 1) / kTile;
@@ -209,16 +209,29 @@ __global__ void __launch_bounds__(kTile *kRows) plane_transpose_kernel(const flo
 #pragma unroll
     for (int r = 0; r < kTile; r += kRows) {
         const int h = h0 + ty + r, w = w0 + tx;
-        if (h < H && w < W) tile[ty + r][tx] = s[(int64_t)h * W + w];
+        tile[ty + r][tx] = (h < H && w < W) ? s[(int64_t)h * W + w] : 0.f;
     }
     __syncthreads();
+    if constexpr (VEC) {
+        // H % 4 == 0: every thread moves 4 consecutive h of one destination row as one 128-bit access; 8 lanes cover a
+        // 128-byte line, a warp 4 destination rows.  tile[h4 + i][wl]: bank = (h4 + i + wl) % 32 — conflict-free.
+        const int t = ty * kTile + tx, wl = t / 8, h4 = (t % 8) * 4;
+        const int w = w0 + wl, h = h0 + h4;
+        if (w < W && h < H) {
+            float4 v = make_float4(tile[h4][wl], tile[h4 + 1][wl], tile[h4 + 2][wl], tile[h4 + 3][wl]);
+            float4 *q = reinterpret_cast<float4 *>(d + (int64_t)w * H + h);
+            if (ACC) { const float4 o = *q; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
+            *q = v;
+        }
+    } else {
 #pragma unroll
-    for (int r = 0; r < kTile; r += kRows) {
-        const int w = w0 + ty + r, h = h0 + tx;
-        if (h < H && w < W) {
-            float *q = d + (int64_t)w * H + h;
-            if (ACC) *q += tile[tx][ty + r];
-            else *q = tile[tx][ty + r];
+        for (int r = 0; r < kTile; r += kRows) {
+            const int w = w0 + ty + r, h = h0 + tx;
+            if (h < H && w < W) {
+                float *q = d + (int64_t)w * H + h;
+                if (ACC) *q += tile[tx][ty + r];
+                else *q = tile[tx][ty + r];
+            }
         }
     }
 }
@@ -227,8 +240,15 @@ int plane_transpose(const float *src, float *dst, int64_t planes, int H, int W, 
     const int64_t tiles = (int64_t)((W + kTile - 1) / kTile) * ((H + kTile - 1) / kTile);
     if (planes * tiles > 0x7fffffffLL) return SS2D_EINVAL;
     const dim3 blk(kTile, kRows);
-    if (acc) plane_transpose_kernel<true><<<(unsigned)(planes * tiles), blk, 0, stream>>>(src, dst, H, W);
-    else plane_transpose_kernel<false><<<(unsigned)(planes * tiles), blk, 0, stream>>>(src, dst, H, W);
+    const bool vec = H % 4 == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0;
+    const unsigned grid = (unsigned)(planes * tiles);
+    if (acc) {
+        if (vec) plane_transpose_kernel<true, true><<<grid, blk, 0, stream>>>(src, dst, H, W);
+        else plane_transpose_kernel<true, false><<<grid, blk, 0, stream>>>(src, dst, H, W);
+    } else {
+        if (vec) plane_transpose_kernel<false, true><<<grid, blk, 0, stream>>>(src, dst, H, W);
+        else plane_transpose_kernel<false, false><<<grid, blk, 0, stream>>>(src, dst, H, W);
+    }
     return (int)cudaGetLastError();
 }
 
