@@ -298,26 +298,30 @@ def main():
                 dev_in[slot][k].copy_(host[k], non_blocking=True)
             ready[slot].record(copy_stream)
 
-    def compute(slot):
+    last_res = []
+
+    def compute(slot, kernels=True):
         with torch.cuda.stream(comp_stream):
             comp_stream.wait_event(ready[slot])
             dd = dev_in[slot]
             a = (dd["u"], dd["delta"], dd["A"], dd["B"], dd["C"], dd["D"], dd["delta_bias"])
-            o, xx, ck, _ = scan_fwd(*a, True, 1, True)
-            g = scan_bwd(*a, dd["dout"], xx, True, 1, ckpt=ck)
+            if kernels:
+                o, xx, ck, _ = scan_fwd(*a, True, 1, True)
+                g = scan_bwd(*a, dd["dout"], xx, True, 1, ckpt=ck)
+                last_res[:] = [(o,) + tuple(g[:7])]
             freed[slot].record(comp_stream)
-            res = (o,) + tuple(g[:7])
+            res = last_res[0]
             if not res_host:
                 res_host.extend(torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in res)
             for h, t in zip(res_host, res):
                 h.copy_(t, non_blocking=True)
 
-    def e2e_run(n):
+    def e2e_run(n, kernels=True):
         copy_in(0)
         for i in range(n):
             if i + 1 < n:
                 copy_in((i + 1) & 1)
-            compute(i & 1)
+            compute(i & 1, kernels)
         comp_stream.synchronize()
         copy_stream.synchronize()
 
@@ -331,7 +335,14 @@ def main():
     barrier()
     e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps  # host clock around a fully synchronised region
     e2e_ms = max_over_ranks(e2e_ms, dev)
-    e2e = {"value": (fb + bb) * world / (e2e_ms * 1e-3) / 1e9, "unit": "GB/s", "ms_per_step": e2e_ms,
+    # the same copies with the kernels left out: the host-side ceiling of this boundary (PCIe per GPU; at N > 1 all ranks
+    # copy to / from pinned memory behind one NUMA node at once)
+    barrier()
+    t0 = time.perf_counter()
+    e2e_run(e2e_steps, kernels=False)
+    barrier()
+    copy_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / e2e_steps, dev)
+    e2e = {"value": (fb + bb) * world / (e2e_ms * 1e-3) / 1e9, "unit": "GB/s", "ms_per_step": e2e_ms, "copies_only_ms_per_step": copy_ms,
            "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": sum(t.numel() * t.element_size() for t in res_host),
            "d2h": "out, du, ddelta, dA, dB, dC, dD, ddelta_bias (every result tensor of the step)"}
 
