@@ -284,9 +284,11 @@ def main():
     res_names = ("out", "du", "ddelta", "dA", "dB", "dC", "dD", "ddelta_bias")
     res_host = []
 
-    # two device input sets: the H2D copy of step i+1 (copy stream) overlaps the kernels of step i (compute stream);
+    # two device input sets: the H2D copy of step i+1 (copy stream) overlaps the kernels of step i (compute stream) and the
+    # D2H of step i-1 (result stream);
     # every step still copies all of its inputs from pinned host memory and reads its result back
-    copy_stream, comp_stream = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    copy_stream, comp_stream, d2h_stream = torch.cuda.Stream(dev), torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    done = torch.cuda.Event()  # results of the last computed step are complete
     dev_in = [{k: torch.empty_like(host[k], device=dev) for k in names} for _ in range(2)]
     ready = [torch.cuda.Event() for _ in range(2)]   # inputs of slot s have arrived
     freed = [torch.cuda.Event() for _ in range(2)]   # kernels reading slot s are done
@@ -310,10 +312,15 @@ def main():
                 g = scan_bwd(*a, dd["dout"], xx, True, 1, ckpt=ck)
                 last_res[:] = [(o,) + tuple(g[:7])]
             freed[slot].record(comp_stream)
-            res = last_res[0]
-            if not res_host:
-                res_host.extend(torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in res)
+            done.record(comp_stream)
+        res = last_res[0]
+        if not res_host:
+            res_host.extend(torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in res)
+        # results leave on their own stream: the D2H of step i overlaps the kernels of step i+1 and the H2D of step i+2
+        with torch.cuda.stream(d2h_stream):
+            d2h_stream.wait_event(done)
             for h, t in zip(res_host, res):
+                t.record_stream(d2h_stream)
                 h.copy_(t, non_blocking=True)
 
     def e2e_run(n, kernels=True):
@@ -324,6 +331,7 @@ def main():
             compute(i & 1, kernels)
         comp_stream.synchronize()
         copy_stream.synchronize()
+        d2h_stream.synchronize()
 
     for ev in freed:
         ev.record(comp_stream)
