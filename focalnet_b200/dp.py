@@ -39,6 +39,7 @@ class FlatBucket:
             offs.append(n)
             n += (p.numel() + 3) // 4 * 4
         self.numel = n
+        self._offs = offs
         self.payload = sum(p.numel() for p in self.params)
         self.flat_param = torch.zeros(n, device=dev, dtype=torch.float32)
         self.flat_grad = torch.zeros(n, device=dev, dtype=torch.float32)
@@ -75,7 +76,19 @@ class FlatBucket:
         return hook
 
     def begin_step(self):
-        """Call before the forward of every step (gradients were zeroed by the optimizer kernel, or by zero_())."""
+        """Call before the forward of every step (gradients were zeroed by the optimizer kernel, or by zero_()).  A caller
+        that dropped the gradient views (``model.zero_grad(set_to_none=True)``, ``p.grad = None``) gets them re-homed: a
+        gradient that autograd allocated elsewhere would silently bypass the all-reduce and the optimizer."""
+        base, end = self.flat_grad.data_ptr(), self.flat_grad.data_ptr() + 4 * self.numel
+        for p, o in zip(self.params, self._offs):
+            g = p.grad
+            if g is None or not (base <= g.data_ptr() < end):
+                view = self.flat_grad[o:o + p.numel()].view_as(p)
+                if g is not None:
+                    view.copy_(g)
+                else:
+                    view.zero_()
+                p.grad = view
         self._pending = list(self._seg_total)
         self._works = []
 

@@ -73,4 +73,8 @@ def test_flat_bucket_single_process_views_follow_updates():
     m(torch.randn(2, 7)).sum().backward()
     assert float(b.flat_grad.abs().sum()) > 0                               # autograd accumulated into the flat buffer
     b.finish_reduce()                                                        # world 1: nothing to wait for
+    m.zero_grad(set_to_none=True)                                            # a caller drops the views ...
+    b.begin_step()                                                           # ... and gets them re-homed
+    assert all(p.grad is not None and b.flat_grad.data_ptr() <= p.grad.data_ptr() < b.flat_grad.data_ptr() + 4 * b.numel
+               for p in m.parameters()) and float(b.flat_grad.abs().sum()) == 0
     assert ring_allreduce_wire_bytes(1000, 1) == 0 and ring_allreduce_wire_bytes(1000, 8) == 1750.0

@@ -21,8 +21,6 @@ def _bind_reference(model):
             model.eval()
             model(torch.rand(1, 3, 32, 32, device="cuda"))
         return "triton"
-    except RuntimeError:
-        raise
     except Exception:  # Triton JIT unavailable: the torch CrossScan / CrossMerge compute the same thing (vmamba_layers.py:29-71)
         H.bind_reference_cuda(model, triton_cross=False)
         return "torch"
