@@ -74,7 +74,7 @@ def train_leg(dev, rank, world, steps, warmup, barrier, max_over_ranks, with_ref
         b.record()
         exposed.append((a, b))
         opt.step()
-        return loss
+        return loss.detach()
 
     for _ in range(warmup):
         step()
