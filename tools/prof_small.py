@@ -14,4 +14,11 @@ ym = torch.randn(B, D, L, device="cuda", requires_grad=True)
 zz = torch.randn(B, H, W, D, device="cuda", requires_grad=True)
 lw, lb = torch.ones(D, device="cuda", requires_grad=True), torch.zeros(D, device="cuda", requires_grad=True)
 om = merge_norm_gate(ym, lw, lb, 1e-5, z=zz); om.backward(torch.randn_like(om))
+from focalnet_b200.ss2d import DtProjFn
+from focalnet_b200 import _lib
+xd = torch.randn(B, 4, 38, L, device="cuda", requires_grad=True)
+Wd = torch.randn(4, D, 6, device="cuda", requires_grad=True)
+od = DtProjFn.apply(xd[:, :, :6], Wd); od.backward(torch.randn_like(od))
+yt = torch.empty(B * D, W, H, device="cuda")
+_lib.lib().ss2d_plane_transpose(x.data_ptr(), yt.data_ptr(), B * D, H, W, 0, torch.cuda.current_stream().cuda_stream)
 torch.cuda.synchronize(); print("ok")
