@@ -224,12 +224,6 @@ static int launch_fwd(const ss2d_scan_fwd_params &p, cudaStream_t stream, CrossI
     using FT = BCTile<in_t, T, SB>;
     constexpr int SLOTS = FT::chunk / SS2D_CKPT_STEPS;
     const int per_g = (int)(p.dim / p.ngroups);
-    if constexpr (NW == 8 && sizeof(in_t) == 4) {
-        // small problems (full-resolution inference at batch 1: 768 sequences = 96 CTAs of 8 warps for 148 SMs): CTAs of 4
-        // channels put work on every SM; the group's B / C tile is then staged by twice as many CTAs (L2 hits)
-        if (p.batch * (xinfo.g_only >= 0 ? 1 : p.ngroups) * ((per_g + 7) / 8) < 2 * 148 && per_g > 4)
-            return launch_fwd<in_t, out_t, CROSS, T, 4, 4, SB>(p, stream, xinfo);
-    }
     const int tiles = (per_g + NW - 1) / NW;
     const bool small_n = p.dstate <= 16;
     const int NS = small_n ? 16 : (((int)p.dstate + 3) & ~3);
