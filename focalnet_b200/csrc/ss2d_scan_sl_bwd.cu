@@ -58,12 +58,8 @@ template <typename in_t, typename out_t, int SN, int NW> struct BwdSmem {
 // forwards / backwards) or from their transposed copies aux.uT / aux.doutT (directions 1 / 3); du is accumulated
 // (red.global.add) into dx[b,d] resp. dx^T (aux.accT) — CrossMerge.backward and CrossScan.backward as load / store
 // addressing over contiguous runs.  ddelta, dB, dC stay in scan order.
-// RA ("recompute a"): the block's 16 a_t are not kept from F to R but evaluated again in R (a second ex2 per (element,
-// state); the MUFU pipe is 20 % busy) — 32 registers less, 4 instead of 3 CTAs per SM.  At full occupancy the kernel is
-// latency-bound (ncu at B=32, L=16384: issue 57 %, shared-memory pipe 68 %, 27 % short-scoreboard stalls with 3 warps per
-// sub-partition), so the launcher takes this variant whenever the grid can fill 4 CTAs on every SM.
-template <typename in_t, typename out_t, int SN, int NW, bool FAST, bool CROSS = false, bool RA = false>
-__global__ void __launch_bounds__(NW *kWarp, RA ? 4 : 3)
+template <typename in_t, typename out_t, int SN, int NW, bool FAST, bool CROSS = false>
+__global__ void __launch_bounds__(NW *kWarp, 3)
 sl_bwd_kernel(const ss2d_scan_bwd_params pb, const int tiles_per_group, const Flags fl, const CrossAux aux) {
     static_assert(!CROSS || (FAST && sizeof(in_t) == 4 && sizeof(out_t) == 4), "fused seam: fp32, aligned, L % 16 == 0");
     using M = Map<SN>;
@@ -365,7 +361,7 @@ sl_bwd_kernel(const ss2d_scan_bwd_params pb, const int tiles_per_group, const Fl
         float hcur[SN];
         hcur[0] = hin.x; hcur[1] = hin.y;
         if constexpr (SN == 4) { hcur[2] = hin.z; hcur[3] = hin.w; }
-        float2 a2[RA ? 1 : SN][RA ? 1 : BK / 2], H2[SN][BK / 2];
+        float2 a2[SN][BK / 2], H2[SN][BK / 2];
 #pragma unroll
         for (int q = 0; q < NQ; ++q) {
             const float4 dlq = xc[q * CPW], duq = xc[(NQ + q) * CPW];
@@ -385,7 +381,7 @@ sl_bwd_kernel(const ss2d_scan_bwd_params pb, const int tiles_per_group, const Fl
                 h1.x = fmaf(a1.x, h0.y, b1.x);
                 h1.y = fmaf(a1.y, h1.x, b1.y);
                 hcur[s] = h1.y;
-                if constexpr (!RA) { a2[s][2 * q] = a0; a2[s][2 * q + 1] = a1; }
+                a2[s][2 * q] = a0; a2[s][2 * q + 1] = a1;
                 H2[s][2 * q] = h0; H2[s][2 * q + 1] = h1;
             }
         }
@@ -408,15 +404,7 @@ sl_bwd_kernel(const ss2d_scan_bwd_params pb, const int tiles_per_group, const Fl
                 const float2 B0 = make_float2(Bv[0], Bv[1]), B1 = make_float2(Bv[2], Bv[3]);
                 const float2 gc0 = __fmul2_rn(go0, make_float2(Cv[0], Cv[1])), gc1 = __fmul2_rn(go1, make_float2(Cv[2], Cv[3]));
                 const float2 h0 = H2[s][2 * q], h1 = H2[s][2 * q + 1];
-                float2 a0, a1;
-                if constexpr (RA) {
-                    const float2 A2d = make_float2(A2[s], A2[s]);
-                    const float2 e0 = __fmul2_rn(dl0, A2d), e1 = __fmul2_rn(dl1, A2d);
-                    a0 = make_float2(ex2(e0.x), ex2(e0.y));
-                    a1 = make_float2(ex2(e1.x), ex2(e1.y));
-                } else {
-                    a0 = a2[s][2 * q]; a1 = a2[s][2 * q + 1];
-                }
+                const float2 a0 = a2[s][2 * q], a1 = a2[s][2 * q + 1];
                 float2 x0, x1;  // dx of the 4 steps
                 x1.y = fmaf(anext[s], dx[s], gc1.y);
                 x1.x = fmaf(a1.y, x1.y, gc1.x);
@@ -513,18 +501,11 @@ static int launch_bwd_t(const ss2d_scan_bwd_params &pb, cudaStream_t stream, Cro
         kern<<<(unsigned)grid, NW * kWarp, SM::total, stream>>>(pb, tiles, fl, xi);
         return (int)cudaGetLastError();
     };
-    static const int sms = [] {
-        int dev = 0, n = 148;
-        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-        return n;
-    }();
-    const bool full = grid >= 4LL * sms;  // enough CTAs to put 4 on every SM: the 128-register variant (RA) pays
     if constexpr (CROSS) {
         if (!fast) return SS2D_ESTRIDE;  // covered problem (cross_covered) with a gradient buffer that is not 16-byte aligned
-        return full ? go(sl_bwd_kernel<in_t, out_t, SN, NW, true, true, true>) : go(sl_bwd_kernel<in_t, out_t, SN, NW, true, true, false>);
+        return go(sl_bwd_kernel<in_t, out_t, SN, NW, true, true>);
     } else {
-        if (fast) return full ? go(sl_bwd_kernel<in_t, out_t, SN, NW, true, false, true>) : go(sl_bwd_kernel<in_t, out_t, SN, NW, true, false, false>);
-        return go(sl_bwd_kernel<in_t, out_t, SN, NW, false>);
+        return fast ? go(sl_bwd_kernel<in_t, out_t, SN, NW, true>) : go(sl_bwd_kernel<in_t, out_t, SN, NW, false>);
     }
 }
 
