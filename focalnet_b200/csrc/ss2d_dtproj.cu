@@ -128,69 +128,6 @@ __global__ void __launch_bounds__(kDtThreads) dt_proj_bwd_w_kernel(const float *
     }
 }
 
-// One-pass backward: a CTA owns (b, k, a tile of kDtThreads * 8 steps) and streams the D rows of dout ONCE.  Per row d every
-// thread adds W[d, r] * g into its R x 8 accumulators of d_dtlr and forms the R partial dot products g . dtlr_r over its 8
-// steps; those are summed over the warp by shuffles and over the CTA's warps in shared memory (one red.shared per warp,
-// row and r); the CTA's (D, R) block of dW leaves with one atomicAdd per entry at the end.
-template <int R>
-__global__ void __launch_bounds__(kDtThreads, 2) dt_proj_bwd_fused_kernel(const float *__restrict__ dout, const float *__restrict__ dtlr,
-                                                                      const float *__restrict__ W, float *__restrict__ dx,
-                                                                      float *__restrict__ dW, const DtGeom g) {
-    extern __shared__ float sm[];  // [D][R] W of this direction | [D][R] dW partial sums of this CTA
-    float *sW = sm, *sdW = sm + g.D * R;
-    const int k = blockIdx.y, b = blockIdx.z, lane = threadIdx.x & 31;
-    for (int i = threadIdx.x; i < (int)g.D * R; i += kDtThreads) { sW[i] = __ldg(W + (int64_t)k * g.D * R + i); sdW[i] = 0.f; }
-    __syncthreads();
-    const int64_t l = ((int64_t)blockIdx.x * kDtThreads + threadIdx.x) * 8;
-    const bool live = l < g.L;  // L % 8 == 0 on this path
-    float4 x0[R], x1[R], a0[R], a1[R];
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-        const float4 *xp = reinterpret_cast<const float4 *>(dtlr + b * g.sb + k * g.sk + r * g.sr + (live ? l : 0));
-        x0[r] = live ? __ldg(xp) : make_float4(0.f, 0.f, 0.f, 0.f);
-        x1[r] = live ? __ldg(xp + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
-        a0[r] = make_float4(0.f, 0.f, 0.f, 0.f);
-        a1[r] = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-    const float *gp = dout + ((int64_t)b * g.K + k) * g.D * g.L + (live ? l : 0);
-#pragma unroll 2
-    for (int d = 0; d < (int)g.D; ++d) {
-        float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
-        if (live) {
-            v0 = __ldg(reinterpret_cast<const float4 *>(gp + (int64_t)d * g.L));
-            v1 = __ldg(reinterpret_cast<const float4 *>(gp + (int64_t)d * g.L) + 1);
-        }
-        float p[R];
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-            const float w = sW[d * R + r];
-            a0[r].x = fmaf(w, v0.x, a0[r].x); a0[r].y = fmaf(w, v0.y, a0[r].y); a0[r].z = fmaf(w, v0.z, a0[r].z); a0[r].w = fmaf(w, v0.w, a0[r].w);
-            a1[r].x = fmaf(w, v1.x, a1[r].x); a1[r].y = fmaf(w, v1.y, a1[r].y); a1[r].z = fmaf(w, v1.z, a1[r].z); a1[r].w = fmaf(w, v1.w, a1[r].w);
-            p[r] = fmaf(v0.x, x0[r].x, fmaf(v0.y, x0[r].y, fmaf(v0.z, x0[r].z, v0.w * x0[r].w))) +
-                   fmaf(v1.x, x1[r].x, fmaf(v1.y, x1[r].y, fmaf(v1.z, x1[r].z, v1.w * x1[r].w)));
-        }
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-#pragma unroll
-            for (int m = 16; m >= 1; m >>= 1) p[r] += __shfl_xor_sync(0xffffffffu, p[r], m);
-        }
-        if (lane == 0) {
-#pragma unroll
-            for (int r = 0; r < R; ++r) atomicAdd(sdW + d * R + r, p[r]);
-        }
-    }
-    if (live) {
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-            float4 *o = reinterpret_cast<float4 *>(dx + (((int64_t)b * g.K + k) * R + r) * g.L + l);
-            o[0] = a0[r];
-            o[1] = a1[r];
-        }
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < (int)g.D * R; i += kDtThreads) atomicAdd(dW + (int64_t)k * g.D * R + i, sdW[i]);
-}
-
 static int dt_geom(DtGeom &g, int64_t B, int64_t K, int64_t D, int64_t R, int64_t L, int64_t sb, int64_t sk, int64_t sr, const void *a,
                    const void *b) {
     if (B <= 0 || K <= 0 || D <= 0 || R <= 0 || R > 8 || L <= 0 || D > kDtMaxD) return SS2D_EINVAL;
@@ -213,14 +150,6 @@ template <int R> static int dt_fwd_t(const float *dtlr, const float *W, float *o
     return (int)cudaGetLastError();
 }
 template <int R> static int dt_bwd_t(const float *dout, const float *dtlr, const float *W, float *dx, float *dW, DtGeom g, cudaStream_t s) {
-    if (g.L % 8 == 0) {  // one pass over dout (two 128-bit pieces per thread and row)
-        const int64_t lt8 = (g.L / 8 + kDtThreads - 1) / kDtThreads;
-        if (lt8 * g.K * g.B >= 2 * 148) {  // enough CTAs; smaller problems keep the two-pass form (more parallelism)
-            dt_proj_bwd_fused_kernel<R><<<dim3((unsigned)lt8, (unsigned)g.K, (unsigned)g.B), kDtThreads, 2 * g.D * R * sizeof(float), s>>>(
-                dout, dtlr, W, dx, dW, g);
-            return (int)cudaGetLastError();
-        }
-    }
     const int64_t ltiles = (g.L / 4 + kDtThreads - 1) / kDtThreads;
     dt_proj_bwd_x_kernel<R><<<dim3((unsigned)ltiles, (unsigned)g.K, (unsigned)g.B), kDtThreads, g.D * R * sizeof(float), s>>>(dout, W, dx, g);
     const int64_t units = g.B * g.K * ((g.D + kDtRows - 1) / kDtRows), wpb = kDtThreads / kWarp;
