@@ -4,11 +4,13 @@ One process per GPU (torchrun), the batch axis is the only partition: every rank
 crops; the ONE exchange step of the path is the gradient all-reduce (2,541,673 fp32 = 10.17 MB), followed by the global-
 norm clip at 0.001 and Adam of ITS/train.py:89-91.
 
-* ``FlatBucket`` re-homes every parameter and its gradient as views into two flat fp32 buffers (parameters in reverse
-  registration order ~ the order the backward produces their gradients), split into a few contiguous segments.  A
-  post-accumulate-grad hook per parameter counts a segment down; when the last gradient of a segment has landed, its
+* ``FlatBucket`` re-homes every parameter as a view into a flat fp32 buffer and owns a flat gradient buffer of the same
+  layout (parameters in reverse registration order ~ the order the backward produces their gradients), split into a few
+  contiguous segments.  A post-accumulate-grad hook per parameter counts a segment down; when the last gradient of a
+  segment has landed, the segment's gradients are gathered into the flat buffer by ONE multi-tensor copy and its
   all-reduce (SUM) is issued asynchronously — NCCL runs it on its own stream while the backward keeps going, so only the
-  last segment's ~tens of microseconds can be exposed.
+  last segment's ~tens of microseconds can be exposed.  (Pre-setting ``p.grad`` to views of the flat buffer would make
+  autograd accumulate with one tiny ``add_`` kernel per parameter: 270 launches, 4 ms of a 195 ms step.)
 * ``FusedClipAdam`` is the optimizer side: the C ABI's ``ss2d_optim_clip_adam`` (two launches over the flat bucket:
   deterministic sum of squares, then clip + Adam + zero-grad; 1 / world size folded in).  CUDA only — no fallback.
 """
@@ -43,11 +45,13 @@ class FlatBucket:
         self.payload = sum(p.numel() for p in self.params)
         self.flat_param = torch.zeros(n, device=dev, dtype=torch.float32)
         self.flat_grad = torch.zeros(n, device=dev, dtype=torch.float32)
+        self._gviews = []
         with torch.no_grad():
             for p, o in zip(self.params, offs):
                 self.flat_param[o:o + p.numel()].view_as(p).copy_(p)
                 p.data = self.flat_param[o:o + p.numel()].view_as(p)
-                p.grad = self.flat_grad[o:o + p.numel()].view_as(p)   # autograd accumulates in place into the view
+                p.grad = None                                         # autograd hands over its own tensor: no add_ kernel
+                self._gviews.append(self.flat_grad[o:o + p.numel()].view_as(p))
         # contiguous segments of roughly equal size, cut at parameter boundaries
         segments = max(1, min(segments, len(self.params)))
         target, self.seg_bounds, self._seg_of, cur = n / segments, [], [], 0
@@ -61,49 +65,50 @@ class FlatBucket:
         self._seg_total = [self._seg_of.count(s) for s in range(len(self.seg_bounds))]
         self._pending = list(self._seg_total)
         self._works: list = []
-        self._hooks = []
-        if self.world > 1:
-            for i, p in enumerate(self.params):
-                self._hooks.append(p.register_post_accumulate_grad_hook(self._make_hook(self._seg_of[i])))
+        self._seg_members = [[i for i, sg in enumerate(self._seg_of) if sg == s] for s in range(len(self.seg_bounds))]
+        self._hooks = [p.register_post_accumulate_grad_hook(self._make_hook(self._seg_of[i])) for i, p in enumerate(self.params)]
 
     # ---- backward-side: launch a segment's all-reduce as soon as its last gradient has been accumulated -------------
+    def _flush_segment(self, seg):
+        """Gather the segment's gradients into the flat buffer (one multi-tensor copy; a parameter without a gradient keeps
+        the zeros the optimizer kernel left) and launch its all-reduce."""
+        idx = [i for i in self._seg_members[seg] if self.params[i].grad is not None]
+        if idx:
+            with torch.no_grad():
+                torch._foreach_copy_([self._gviews[i] for i in idx], [self.params[i].grad for i in idx])
+        if self.world > 1:
+            a, b = self.seg_bounds[seg]
+            self._works.append(dist.all_reduce(self.flat_grad[a:b], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+        self._pending[seg] = 0
+
     def _make_hook(self, seg):
         def hook(_param):
             self._pending[seg] -= 1
             if self._pending[seg] == 0:
-                a, b = self.seg_bounds[seg]
-                self._works.append(dist.all_reduce(self.flat_grad[a:b], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+                self._flush_segment(seg)
         return hook
 
     def begin_step(self):
-        """Call before the forward of every step (gradients were zeroed by the optimizer kernel, or by zero_()).  A caller
-        that dropped the gradient views (``model.zero_grad(set_to_none=True)``, ``p.grad = None``) gets them re-homed: a
-        gradient that autograd allocated elsewhere would silently bypass the all-reduce and the optimizer."""
-        base, end = self.flat_grad.data_ptr(), self.flat_grad.data_ptr() + 4 * self.numel
-        for p, o in zip(self.params, self._offs):
-            g = p.grad
-            if g is None or not (base <= g.data_ptr() < end):
-                view = self.flat_grad[o:o + p.numel()].view_as(p)
-                if g is not None:
-                    view.copy_(g)
-                else:
-                    view.zero_()
-                p.grad = view
+        """Call before the forward of every step: drops last step's gradient tensors (their values were consumed from the
+        flat buffer, which the optimizer kernel zeroed) and re-arms the segment counters."""
+        for p in self.params:
+            p.grad = None
         self._pending = list(self._seg_total)
         self._works = []
 
     def finish_reduce(self):
-        """Make the current stream wait for the all-reduces issued during the backward (stream-level wait, the host does
-        not block).  Segments whose hook did not fire (a parameter that received no gradient) are reduced here."""
-        if self.world > 1:
-            for seg, left in enumerate(self._pending):
-                if left > 0:
-                    a, b = self.seg_bounds[seg]
-                    self._works.append(dist.all_reduce(self.flat_grad[a:b], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
-                    self._pending[seg] = 0
-            for w in self._works:
-                w.wait()
+        """After the backward: flush the segments whose last hook did not fire (a parameter that received no gradient), then
+        make the current stream wait for the all-reduces (stream-level wait, the host does not block)."""
+        for seg, left in enumerate(self._pending):
+            if left > 0:
+                self._flush_segment(seg)
+        for w in self._works:
+            w.wait()
         self._works = []
+
+    def grad_view(self, p):
+        """The slice of the flat gradient buffer that belongs to parameter `p` (what the optimizer kernel reads)."""
+        return self._gviews[next(i for i, q in enumerate(self.params) if q is p)]
 
     def allreduce_whole(self):
         """One blocking-on-stream all-reduce of the whole bucket (what `allreduce_ms` times)."""

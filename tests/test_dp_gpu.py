@@ -24,7 +24,7 @@ def test_fused_clip_adam_matches_torch(max_norm):
     for step in range(4):
         grads = [torch.randn_like(p) * (0.1 if step % 2 else 3.0) for p in ours]
         for p, q, g in zip(ours, theirs, grads):
-            p.grad.copy_(g)
+            b.grad_view(p).copy_(g)
             q.grad = g.clone()
         norm_ref = torch.nn.utils.clip_grad_norm_(theirs, max_norm) if max_norm > 0 else None
         ref.step()
@@ -33,7 +33,7 @@ def test_fused_clip_adam_matches_torch(max_norm):
             assert rel_err(opt.last_norm, norm_ref.view(1)) < 1e-5
         for p, q in zip(ours, theirs):
             assert rel_err(p, q) < 1e-5
-            assert float(p.grad.abs().max()) == 0.0           # zero_grad folded into the pass
+            assert float(b.grad_view(p).abs().max()) == 0.0   # zero_grad folded into the pass
     assert rel_err(opt.exp_avg[: ours[-1].numel()], ref.state[theirs[-1]]["exp_avg"].flatten()) < 1e-5  # reversed order
 
 
@@ -66,7 +66,7 @@ def test_dp_train_step_matches_reference_step_on_the_unchanged_model():
         gmax = max(float(q.grad.abs().max()) for q in twin.parameters())
         for (n, p), q in zip(model.named_parameters(), twin.parameters()):
             assert rel_err(p.grad, q.grad, floor=1e-2 * gmax) < 1e-3, n  # = rtol 1e-3 + atol 1e-5 * gmax: analytically-zero gradients hold rounding noise
-            p.grad.copy_(q.grad)   # identical inputs for the optimizer comparison (Adam's m / sqrt(v) amplifies noise-level grads)
+            bucket.grad_view(p).copy_(q.grad)   # identical inputs for the optimizer comparison (Adam's m / sqrt(v) amplifies noise-level grads)
         torch.nn.utils.clip_grad_norm_(twin.parameters(), 0.001)
         opt_ref.step()
         opt.step()
