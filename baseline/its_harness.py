@@ -200,5 +200,36 @@ def psnr(pred, label):
     return float(10 * torch.log10(1 / F.mse_loss(torch.clamp(pred, 0, 1), label)))
 
 
+def ssim(x, y, data_range: float = 1.0, win_size: int = 11, sigma: float = 1.5):
+    """Structural similarity with the published default recipe (Wang et al. 2004; what pytorch_msssim.ssim computes, which
+    ITS/eval.py:49-52 calls and this image lacks): separable Gaussian window 11 / sigma 1.5, 'valid' filtering, K = (0.01,
+    0.03), mean over channels and pixels -> one value per image."""
+    coords = torch.arange(win_size, dtype=x.dtype, device=x.device) - win_size // 2
+    g = torch.exp(-(coords ** 2) / (2 * sigma ** 2))
+    g = (g / g.sum())
+    C = x.shape[1]
+
+    def blur(t):
+        t = F.conv2d(t, g.view(1, 1, 1, -1).repeat(C, 1, 1, 1), groups=C)
+        return F.conv2d(t, g.view(1, 1, -1, 1).repeat(C, 1, 1, 1), groups=C)
+
+    c1, c2 = (0.01 * data_range) ** 2, (0.03 * data_range) ** 2
+    mx, my = blur(x), blur(y)
+    sxx, syy, sxy = blur(x * x) - mx * mx, blur(y * y) - my * my, blur(x * y) - mx * my
+    cs = (2 * sxy + c2) / (sxx + syy + c2)
+    return (((2 * mx * my + c1) / (mx * mx + my * my + c1)) * cs).flatten(1).mean(1)
+
+
+def eval_metrics(pred, label):
+    """ITS/eval.py:43-54: PSNR of the clamped prediction and SSIM after average-pooling both images by
+    max(1, round(min(H, W) / 256)) — on the already cropped prediction.  -> (psnr dB, mean ssim)."""
+    pc = torch.clamp(pred, 0, 1)
+    H, W = pc.shape[2], pc.shape[3]
+    r = max(1, round(min(H, W) / 256))
+    size = (int(H / r), int(W / r))
+    s = ssim(F.adaptive_avg_pool2d(pc, size), F.adaptive_avg_pool2d(label, size), data_range=1.0)
+    return float(10 * torch.log10(1 / F.mse_loss(pc, label))), float(s.mean())
+
+
 def param_count(model) -> int:
     return sum(p.numel() for p in model.parameters())

@@ -133,6 +133,41 @@ class FusedClipAdam:
         self.last_norm = torch.zeros(1, device=bucket.flat_param.device, dtype=torch.float32)
         self.steps = 0
 
+    # ---- checkpoint interop with the reference's training script (ITS/train.py:24-27,110-113 saves / restores
+    # torch.optim.Adam.state_dict()): same dictionary layout, parameters indexed in model.parameters() order -------------
+    def state_dict(self):
+        b = self.b
+        order = list(reversed(range(len(b.params))))  # b.params is reversed registration order
+        state = {}
+        if self.steps > 0:
+            for idx, i in enumerate(order):
+                o, n, p = b._offs[i], b.params[i].numel(), b.params[i]
+                state[idx] = {"step": torch.tensor(float(self.steps)), "exp_avg": self.exp_avg[o:o + n].view_as(p).clone(),
+                              "exp_avg_sq": self.exp_avg_sq[o:o + n].view_as(p).clone()}
+        group = {"lr": self.lr, "betas": tuple(self.betas), "eps": self.eps, "weight_decay": 0, "amsgrad": False, "maximize": False,
+                 "foreach": None, "capturable": False, "differentiable": False, "fused": None, "params": list(range(len(order)))}
+        return {"state": state, "param_groups": [group]}
+
+    def load_state_dict(self, sd):
+        b = self.b
+        order = list(reversed(range(len(b.params))))
+        g = sd["param_groups"][0]
+        if len(g["params"]) != len(order):
+            raise ValueError("optimizer state was saved for a different parameter list")
+        self.lr, self.betas, self.eps = float(g["lr"]), tuple(g["betas"]), float(g["eps"])
+        self.exp_avg.zero_()
+        self.exp_avg_sq.zero_()
+        steps = 0
+        for idx, i in enumerate(order):
+            st = sd["state"].get(idx)
+            if st is None:
+                continue
+            o, n, p = b._offs[i], b.params[i].numel(), b.params[i]
+            self.exp_avg[o:o + n].view_as(p).copy_(st["exp_avg"])
+            self.exp_avg_sq[o:o + n].view_as(p).copy_(st["exp_avg_sq"])
+            steps = max(steps, int(float(st["step"])))
+        self.steps = steps
+
     def step(self, lr: Optional[float] = None):
         self.steps += 1
         b = self.b

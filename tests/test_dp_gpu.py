@@ -75,3 +75,38 @@ def test_dp_train_step_matches_reference_step_on_the_unchanged_model():
     # and the one-call form
     torch.manual_seed(9)
     assert torch.isfinite(dp_train_step(model, bucket, opt, H.its_loss, x, J))
+
+
+def test_optimizer_state_round_trips_with_torch_adam_checkpoints(tmp_path):
+    """ITS/train.py:110-113 saves {'model', 'optimizer': torch.optim.Adam.state_dict(), 'epoch'} and :24-27 restores it: the
+    fused optimizer reads and writes the same dictionary, so a run can move between the reference's optimizer and this one."""
+    from focalnet_b200.dp import FlatBucket, FusedClipAdam
+    torch.manual_seed(3)
+    shapes = [(17, 5), (9,), (4, 3, 3, 3)]
+    theirs = [torch.nn.Parameter(torch.randn(*s, device="cuda")) for s in shapes]
+    ref = torch.optim.Adam(theirs, lr=2e-3, betas=(0.9, 0.999), eps=1e-8)
+    for _ in range(3):
+        for q in theirs:
+            q.grad = torch.randn_like(q)
+        ref.step()
+    path = str(tmp_path / "model.pkl")
+    torch.save({"model": [q.detach().clone() for q in theirs], "optimizer": ref.state_dict(), "epoch": 3}, path)
+    ck = torch.load(path, weights_only=False)
+    ours = [torch.nn.Parameter(t.clone()) for t in ck["model"]]
+    b = FlatBucket(ours)
+    opt = FusedClipAdam(b, lr=1.0, max_norm=0.0)
+    opt.load_state_dict(ck["optimizer"])
+    assert opt.steps == 3 and opt.lr == 2e-3
+    for _ in range(2):  # continue on both sides from identical gradients
+        gs = [torch.randn_like(q) for q in theirs]
+        for p, q, g in zip(ours, theirs, gs):
+            b.grad_view(p).copy_(g)
+            q.grad = g.clone()
+        ref.step()
+        opt.step()
+    for p, q in zip(ours, theirs):
+        assert rel_err(p, q) < 1e-5
+    back = torch.optim.Adam([torch.nn.Parameter(t.detach().clone()) for t in ours], lr=1.0)
+    back.load_state_dict(opt.state_dict())           # and back into the reference's optimizer
+    assert back.param_groups[0]["lr"] == 2e-3 and int(back.state[back.param_groups[0]["params"][0]]["step"]) == 5
+    assert rel_err(back.state[back.param_groups[0]["params"][1]]["exp_avg"], ref.state[theirs[1]]["exp_avg"]) < 1e-5

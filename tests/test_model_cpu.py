@@ -61,3 +61,14 @@ def test_patch_ss2d_rebinds_every_module_of_the_unchanged_model():
         assert mm.forward.func.__name__ == "ss2d_forward"
     assert unpatch_ss2d(m) == 12
     assert all(mm.forward_core is core and mm.forward == fwd for mm, (core, fwd) in zip(mods, orig))
+
+
+def test_eval_metrics_restatement():
+    """PSNR / SSIM of ITS/eval.py:43-54: identical images -> SSIM 1 and infinite PSNR; SSIM falls with noise and is symmetric."""
+    torch.manual_seed(0)
+    a = torch.rand(2, 3, 64, 80)
+    b = (a + 0.1 * torch.randn_like(a)).clamp(0, 1)
+    s_same, s_noisy, s_sym = H.ssim(a, a), H.ssim(a, b), H.ssim(b, a)
+    assert torch.allclose(s_same, torch.ones(2), atol=1e-6) and (s_noisy < 0.95).all() and torch.allclose(s_noisy, s_sym, atol=1e-6)
+    p, s = H.eval_metrics(b, a)
+    assert 15.0 < p < 30.0 and 0.0 < s < 1.0

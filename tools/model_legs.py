@@ -155,7 +155,7 @@ def infer_leg(dev, rank, world, steps, warmup, barrier, max_over_ranks, with_ref
         y = H.eval_forward(model, x)
     out = {"img_s": world * TILES_PER_GPU / (ms * 1e-3), "ms_per_batch": ms, "images_per_gpu": TILES_PER_GPU,
            "image": "620x460 reflect-padded to 640x480 (ITS/eval.py:33-37)", "model": "MIMOUNet g4 (results_1mlp_g4, patch_size_global=4)",
-           "scan_L": [19200, 4800, 1200], "psnr_dB": H.psnr(y, J)}
+           "scan_L": [19200, 4800, 1200], "psnr_dB": H.psnr(y, J), "ssim": H.eval_metrics(y, J)[1]}
     if with_reference and world == 1 and rank == 0:
         try:
             unpatch_ss2d(model)
@@ -163,7 +163,8 @@ def infer_leg(dev, rank, world, steps, warmup, barrier, max_over_ranks, with_ref
             with torch.no_grad():
                 rms = _timed(lambda: H.eval_forward(model, x), max(3, min(steps, 10)), 2, barrier)
                 y_ref = H.eval_forward(model, x)
-            out["reference_kernels"] = {"img_s": TILES_PER_GPU / (rms * 1e-3), "ms_per_batch": rms, "what": how, "psnr_dB": H.psnr(y_ref, J)}
+            out["reference_kernels"] = {"img_s": TILES_PER_GPU / (rms * 1e-3), "ms_per_batch": rms, "what": how, "psnr_dB": H.psnr(y_ref, J),
+                                        "ssim": H.eval_metrics(y_ref, J)[1]}
             out["psnr_delta_dB"] = abs(out["psnr_dB"] - H.psnr(y_ref, J))
             out["speedup_vs_reference_kernels"] = rms / ms
         except Exception as exc:
