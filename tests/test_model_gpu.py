@@ -115,3 +115,22 @@ def test_cross_selective_scan_under_autocast_matches_reference(ref_ready, force_
     assert rel_err(res[1][0], res[0][0]) < 2e-2
     for a, b, k in zip(res[1][1], res[0][1], ("dx", "dx_proj", "ddt_w", "ddt_b", "dA_logs", "dDs")):
         assert rel_err(a, b) < 5e-2, k
+
+
+def test_patched_model_runs_under_autocast(ref_ready):
+    """AMP is not the shipped configuration (ITS/train.py has no autocast), but a user can switch it on: the patched modules
+    then keep the module's own forwardv2 around the fused core in 16 bits.  Forward and backward must run and stay close to
+    the fp32 result."""
+    from focalnet_b200 import patch_ss2d
+    model = H.build_model("g2", "cuda")
+    assert patch_ss2d(model) == 12
+    model.eval()
+    x, J = H.synthetic_pair(2, 64, 64, "cuda", seed=6)
+    y32 = model(x)[2]
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        y16 = model(x)[2]
+        loss = H.its_loss([o.float() for o in model(x)], J)
+    loss.backward()
+    assert torch.isfinite(y16).all() and rel_err(y16.float(), y32) < 5e-2
+    grads = [p.grad for p in model.parameters() if p.grad is not None]
+    assert len(grads) > 200 and all(torch.isfinite(g).all() for g in grads)
