@@ -26,7 +26,7 @@ __device__ __forceinline__ float warp_sum(float v) {
 
 // y:(B,D,L) -> out:(B,L,D);  out = (LN_D(y) * w + b) [* silu(z)]
 template <int NJ>
-__global__ void __launch_bounds__(kMnWarps *kWarp, NJ <= 8 ? 2 : 1) merge_norm_fwd_kernel(const float *__restrict__ y, const float *__restrict__ w,
+__global__ void __launch_bounds__(kMnWarps *kWarp, NJ <= 8 ? 3 : 1) merge_norm_fwd_kernel(const float *__restrict__ y, const float *__restrict__ w,
                                                                          const float *__restrict__ bvec, const float *__restrict__ z,
                                                                          int64_t z_pstride, float *__restrict__ out, int D,
                                                                          int64_t L, float eps, int tiles_per_image) {
