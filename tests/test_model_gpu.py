@@ -134,3 +134,20 @@ def test_patched_model_runs_under_autocast(ref_ready):
     assert torch.isfinite(y16).all() and rel_err(y16.float(), y32) < 5e-2
     grads = [p.grad for p in model.parameters() if p.grad is not None]
     assert len(grads) > 200 and all(torch.isfinite(g).all() for g in grads)
+
+
+def test_cuda_graph_replay_of_the_patched_model_matches_eager(ref_ready):
+    """GraphedForward captures the whole single-image evaluation forward (patched model, no_grad) into one CUDA graph; a
+    replay on new data must equal the eager forward bit for bit (same kernels, same order)."""
+    from focalnet_b200 import GraphedForward, patch_ss2d
+    model = H.build_model("g4", "cuda")
+    patch_ss2d(model)
+    model.eval()
+    x, _ = H.synthetic_pair(2, 200, 264, "cuda", seed=9)
+    gf = GraphedForward(lambda t: H.eval_forward(model, t), x[:1].contiguous())
+    with torch.no_grad():
+        for i in range(2):
+            xi = x[i:i + 1].contiguous()
+            y_graph = gf(xi).clone()
+            y_eager = H.eval_forward(model, xi)
+            assert torch.equal(y_graph, y_eager), float((y_graph - y_eager).abs().max())

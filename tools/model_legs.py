@@ -156,6 +156,21 @@ def infer_leg(dev, rank, world, steps, warmup, barrier, max_over_ranks, with_ref
     out = {"img_s": world * TILES_PER_GPU / (ms * 1e-3), "ms_per_batch": ms, "images_per_gpu": TILES_PER_GPU,
            "image": "620x460 reflect-padded to 640x480 (ITS/eval.py:33-37)", "model": "MIMOUNet g4 (results_1mlp_g4, patch_size_global=4)",
            "scan_L": [19200, 4800, 1200], "psnr_dB": H.psnr(y, J), "ssim": H.eval_metrics(y, J)[1]}
+    # one image per call (ITS/eval.py:19 evaluates with batch_size=1): eager launches vs ONE CUDA-graph replay
+    if world == 1 and rank == 0:
+        try:
+            from focalnet_b200 import GraphedForward
+            x1 = x[:1].contiguous()
+            with torch.no_grad():
+                eager_ms = _timed(lambda: H.eval_forward(model, x1), max(5, steps), 3, barrier)
+                gf = GraphedForward(lambda t: H.eval_forward(model, t), x1)
+                graph_ms = _timed(lambda: gf(x1), max(5, steps), 3, barrier)
+                same = float((gf(x1) - H.eval_forward(model, x1)).abs().max())
+            out["single_image"] = {"eager_ms": eager_ms, "cuda_graph_ms": graph_ms, "img_s_cuda_graph": 1e3 / graph_ms,
+                                   "max_abs_diff_graph_vs_eager": same}
+            del gf
+        except Exception as exc:
+            out["single_image"] = {"error": repr(exc)[:200]}
     if with_reference and world == 1 and rank == 0:
         try:
             unpatch_ss2d(model)
@@ -166,6 +181,9 @@ def infer_leg(dev, rank, world, steps, warmup, barrier, max_over_ranks, with_ref
             out["reference_kernels"] = {"img_s": TILES_PER_GPU / (rms * 1e-3), "ms_per_batch": rms, "what": how, "psnr_dB": H.psnr(y_ref, J),
                                         "ssim": H.eval_metrics(y_ref, J)[1]}
             out["psnr_delta_dB"] = abs(out["psnr_dB"] - H.psnr(y_ref, J))
+            if "single_image" in out and "eager_ms" in out["single_image"]:
+                with torch.no_grad():
+                    out["single_image"]["reference_kernels_eager_ms"] = _timed(lambda: H.eval_forward(model, x[:1].contiguous()), max(5, steps), 3, barrier)
             out["speedup_vs_reference_kernels"] = rms / ms
         except Exception as exc:
             out["reference_kernels"] = {"unavailable": repr(exc)[:200]}
