@@ -30,7 +30,7 @@ int smem_optin_impl(const void *kern, int bytes) {
 extern "C" int ss2d_abi_version(void) { return SS2D_ABI_VERSION; }
 
 extern "C" const char *ss2d_build_info(void) {
-    return "libss2d_b200 abi=3 arch=sm_100a kernels=scan_sl_fwd,scan_sl_bwd,scan_fwd,scan_bwd,cross_scan,cross_merge,cross_scan_fused,dwconv_silu,merge_norm_gate "
+    return "libss2d_b200 abi=3 arch=sm_100a kernels=scan_sl_fwd,scan_sl_bwd,scan_fwd,scan_bwd,cross_scan,cross_merge,cross_scan_fused,dwconv_silu,merge_norm_gate,dt_proj,optim_clip_adam "
            "cuda=" SS2D_STR(__CUDACC_VER_MAJOR__) "." SS2D_STR(__CUDACC_VER_MINOR__);
 }
 
